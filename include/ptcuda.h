@@ -1,0 +1,139 @@
+/*
+ * ptcuda.h -- C ABI of libptcuda, the B200 (sm_100a) replacement for the OpenCL render path of
+ * eriklupander/pathtracer-ocl.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference repo):
+ *
+ *   ptc_device_count / ptc_device_name
+ *        cmd/pt/main.go:98-112 listDevices()  (cl.GetPlatforms()[0].GetDevices(All) + Name()).
+ *   ptc_render
+ *        internal/ocl/ocltracer.go:100-226 Trace() together with :228-254 prepareTextures() and
+ *        :256-376 computeBatch(): device selection, texture packing, the per-4-scanline batch
+ *        loop (buffer upload, SetArgs, NDRange, Finish, readback) and the device kernel
+ *        internal/ocl/tracer.cl:831-1187 trace().  One call renders the whole frame.
+ *   ptc_open / ptc_trace / ptc_read / ptc_close
+ *        the same path split into its phases (scene upload, kernel, gather+readback) so a caller
+ *        can keep a scene resident, time the phases separately, or render one shard of the
+ *        frame per process (one process per GPU).  ptc_render == open + trace + read + close.
+ *
+ * Conventions (kept from the reference boundary):
+ *   - plain pointers and sizes only; every pointer is borrowed for the duration of the call;
+ *   - objects / triangles / groups / camera are the packed records of include/ptwire.h, i.e. the
+ *     exact bytes the Go side passes to EnqueueWriteBuffer (ocltracer.go:312-338);
+ *   - the result is W*H*4 doubles, RGBA, row-major, top row first, alpha = 1.0
+ *     (tracer.cl:1184-1187);
+ *   - the reference draws one random double per pixel on the host (ocltracer.go:260-263); here
+ *     the caller passes them (`seeds`, row-major, one per pixel) so renders are reproducible;
+ *   - errors: the reference aborts via logrus.Fatalf; these functions return non-zero and write
+ *     a message into `err` instead, the Go wrapper turns that back into Fatalf;
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails.
+ *   - thread-compatible: no global mutable state; distinct contexts may be used concurrently.
+ */
+#ifndef PTCUDA_H
+#define PTCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTC_ABI_VERSION 1
+
+/* precision */
+#define PTC_FP32 0   /* fp32 arithmetic mode (north_star: "fp32 mode", tolerance 1e-3 at 1 spp)   */
+#define PTC_FP64 1   /* fp64 arithmetic mode, matches tracer.cl            (tolerance 1e-6 at 1 spp) */
+
+/* rng_mode */
+#define PTC_RNG_PARITY 0 /* canonical noise3D stream, bit-identical to the oracle (oracle/README.md) */
+#define PTC_RNG_FAST   1 /* same hash, hardware-approximated sin; statistically validated only       */
+
+typedef struct ptc_job {
+    int32_t abi_version;          /* must be PTC_ABI_VERSION */
+
+    const void *objects;          /* n_objects  * 1024 B  (ptw_object)   */
+    int32_t     n_objects;        /* 1..16 (tracer.cl:846)               */
+    const void *triangles;        /* n_triangles * 512 B  (ptw_triangle), may be NULL when 0 */
+    int32_t     n_triangles;
+    const void *groups;           /* n_groups   * 256 B  (ptw_group), may be NULL when 0     */
+    int32_t     n_groups;
+    const void *camera;           /* 256 B (ptw_camera)                  */
+
+    /* Texture classes in kernel-argument order (tracer.cl:833): 0 plane textures, 1 sphere maps,
+     * 2 cube-cross maps.  RGBA8, row 0 = top, `layers` images of identical size packed back to
+     * back (ocltracer.go:228-254).  tex[i] == NULL means "class unused". */
+    const uint8_t *tex[3];
+    int32_t        tex_w[3], tex_h[3], tex_layers[3];
+
+    const double *seeds;          /* width*height doubles in [0,1), row-major */
+    int32_t samples;              /* samples per pixel, >= 1 */
+    int32_t precision;            /* PTC_FP32 | PTC_FP64 */
+    int32_t rng_mode;             /* PTC_RNG_PARITY | PTC_RNG_FAST */
+
+    /* Devices driven by THIS process.  NULL/0 => device 0 (the reference's --device-index
+     * default).  With n_devices > 1 the frame is split across them as interleaved scanline
+     * tiles and gathered over NVLink peer copies before the single D2H readback. */
+    const int32_t *devices;
+    int32_t        n_devices;
+
+    /* Frame sharding across PROCESSES (one process per GPU).  Scanline tile k (rows
+     * [k*rows_per_tile, (k+1)*rows_per_tile)) belongs to shard k % shard_count.  shard_count
+     * <= 1 means "whole frame".  A sharded context renders only its own tiles; ptc_read then
+     * returns just those rows, packed in increasing row order. */
+    int32_t shard_index;
+    int32_t shard_count;
+    int32_t rows_per_tile;        /* 0 => 4, the reference's batch height (ocltracer.go:214) */
+
+    int32_t reserved[8];          /* must be zero */
+} ptc_job;
+
+typedef struct ptc_stats {
+    double  upload_ms;            /* host wall time of ptc_open (scene flatten + H2D)          */
+    double  kernel_ms;            /* max over devices of CUDA-event time of the last ptc_trace */
+    double  read_ms;              /* host wall time of the last ptc_read (gather + D2H)        */
+    int64_t h2d_bytes;            /* bytes copied host->device by ptc_open (all devices)       */
+    int64_t d2h_bytes;            /* bytes copied device->host by the last ptc_read            */
+    int64_t p2p_bytes;            /* bytes moved device->device by the last ptc_read           */
+    int64_t paths;                /* pixels_in_shard * samples                                 */
+    int32_t kernel_launches;      /* trace-kernel launches in the last ptc_trace (all devices) */
+    int32_t n_devices;
+    int32_t rows;                 /* rows rendered by this context                             */
+    int32_t reserved;
+} ptc_stats;
+
+typedef struct ptc_context ptc_context;
+
+/* --list-devices support.  ptc_device_count returns the number of CUDA devices (0 if none or if
+ * the driver is unusable).  ptc_device_name returns 0 and a NUL-terminated name, non-zero on a
+ * bad index. */
+int ptc_device_count(void);
+int ptc_device_name(int index, char *buf, int buflen);
+
+/* One-shot drop-in for ocl.Trace().  out_rgba: rows_of_this_shard * width * 4 doubles. */
+int ptc_render(const ptc_job *job, double *out_rgba, char *err, int errlen);
+
+/* Phase API. */
+int  ptc_open(const ptc_job *job, ptc_context **ctx, char *err, int errlen);
+int  ptc_trace(ptc_context *ctx, char *err, int errlen);   /* launches + waits; result stays in HBM */
+int  ptc_read(ptc_context *ctx, double *out_rgba, char *err, int errlen);
+int  ptc_get_stats(const ptc_context *ctx, ptc_stats *stats);
+void ptc_close(ptc_context *ctx);
+
+/* Replace the per-pixel seeds of an open context (width*height doubles, same layout as
+ * ptc_job.seeds).  Mirrors the reference drawing fresh seeds for every batch. */
+int ptc_set_seeds(ptc_context *ctx, const double *seeds, char *err, int errlen);
+
+/* Device-resident result of local device `local_index` (0..n_devices-1): pointer to its packed
+ * rows (rows * width * 4 doubles), for callers that gather on the device themselves (NCCL). */
+int ptc_device_framebuffer(ptc_context *ctx, int local_index, void **dev_ptr, int64_t *n_doubles,
+                           int32_t *cuda_device);
+
+/* Rows owned by this context, in increasing order; returns the count, fills at most `cap`. */
+int ptc_shard_rows(const ptc_context *ctx, int32_t *rows, int cap);
+
+const char *ptc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTCUDA_H */
