@@ -1,0 +1,75 @@
+// rng.cuh -- device implementation of the reference's hash RNG (reference internal/ocl/tracer.cl:314-317)
+//
+//     noise3D(x,y,z) = fract(sin(x*112.9898f + y*179.233f + z*237.212f) * 43758.5453f)
+//
+// PARITY mode evaluates the canonical stream: separately rounded float products/sums and a sine
+// built only from correctly rounded IEEE double operations (mul, fma, round-to-nearest-even
+// conversion), rounded once to float -- every step is exactly reproducible on any IEEE machine,
+// which is what lets a 1-spp render be compared pixel by pixel with a CPU restatement.
+// FAST mode keeps the exact double argument reduction (the argument reaches ~1e9, far outside what
+// fp32 reduction can handle) but evaluates the polynomial in fp32: the stream is statistically the
+// same hash but not bit-identical, so it is validated on converged images only.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ptk {
+
+enum { RNG_PARITY = 0, RNG_FAST = 1 };
+
+__device__ __forceinline__ float sin_parity(float x) {
+    const double INV_PI = 0x1.45f306dc9c883p-2;
+    const double PI_HI = 0x1.921fb54442d18p+1;
+    const double PI_LO = 0x1.1a62633145c07p-53;
+    double xd = (double)x;
+    long long qi = __double2ll_rn(__dmul_rn(xd, INV_PI));
+    double q = (double)qi;
+    double r = __fma_rn(-q, PI_HI, xd);
+    r = __fma_rn(-q, PI_LO, r);
+    double r2 = __dmul_rn(r, r);
+    double p = 0x1.71b8ef6dcf572p-66;
+    p = __fma_rn(p, r2, -0x1.2f49b46814157p-57);
+    p = __fma_rn(p, r2, 0x1.952c77030ad4ap-49);
+    p = __fma_rn(p, r2, -0x1.ae7f3e733b81fp-41);
+    p = __fma_rn(p, r2, 0x1.6124613a86d09p-33);
+    p = __fma_rn(p, r2, -0x1.ae64567f544e4p-26);
+    p = __fma_rn(p, r2, 0x1.71de3a556c734p-19);
+    p = __fma_rn(p, r2, -0x1.a01a01a01a01ap-13);
+    p = __fma_rn(p, r2, 0x1.1111111111111p-7);
+    p = __fma_rn(p, r2, -0x1.5555555555555p-3);
+    double s = __fma_rn(__dmul_rn(r, r2), p, r);
+    if (qi & 1) s = -s;
+    return __double2float_rn(s);
+}
+
+__device__ __forceinline__ float sin_fast(float x) {
+    const double INV_PI = 0x1.45f306dc9c883p-2;
+    const double PI_HI = 0x1.921fb54442d18p+1;
+    const double PI_LO = 0x1.1a62633145c07p-53;
+    double xd = (double)x;
+    int qi = __double2int_rn(xd * INV_PI);       // |x| < 6.7e9 on every call site
+    double q = (double)qi;
+    double rd = __fma_rn(-q, PI_LO, __fma_rn(-q, PI_HI, xd));
+    float r = __double2float_rn(rd);
+    float r2 = r * r;
+    float p = -2.5052108e-8f;
+    p = fmaf(p, r2, 2.7557319e-6f);
+    p = fmaf(p, r2, -1.9841270e-4f);
+    p = fmaf(p, r2, 8.3333333e-3f);
+    p = fmaf(p, r2, -1.6666667e-1f);
+    float s = fmaf(r * r2, p, r);
+    return (qi & 1) ? -s : s;
+}
+
+template <int MODE>
+__device__ __forceinline__ float noise3d(float x, float y, float z) {
+    float a = __fmul_rn(x, 112.9898f);
+    float b = __fmul_rn(y, 179.233f);
+    float c = __fmul_rn(z, 237.212f);
+    float arg = __fadd_rn(__fadd_rn(a, b), c);
+    float s = (MODE == RNG_PARITY) ? sin_parity(arg) : sin_fast(arg);
+    float v = __fmul_rn(s, 43758.5453f);
+    float f = __fsub_rn(v, floorf(v));
+    return fminf(f, 0x1.fffffep-1f);
+}
+
+}  // namespace ptk

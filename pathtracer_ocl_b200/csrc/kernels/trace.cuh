@@ -1,0 +1,565 @@
+// trace.cuh -- the path-tracing kernel for sm_100a.
+//
+// Replaces the reference's OpenCL device kernel `trace` (reference internal/ocl/tracer.cl:831-1187)
+// and every helper on its path.  Same observable behaviour -- camera rays with AA jitter and
+// sunflower depth of field (tracer.cl:745-779, 221-248), plane / sphere / cylinder / cube / BVH
+// triangle intersection (378-483, 598-720), reflect / thin-glass / refract / diffuse branching
+// (982-1061), texture lookups (907-911, 1076-1093), mask-and-accumulate shading (1116-1179), the
+// hash RNG (314-317) -- but organised for a Blackwell SM instead of mirroring the OpenCL source:
+//
+//   * one launch covers the whole frame (the reference enqueues H/4 four-scanline batches);
+//   * a thread owns a pixel (optionally a slice of its samples) and runs ONE flat loop whose
+//     iteration is a path segment: when a lane's path ends it regenerates the next camera ray in
+//     place, so lanes of a warp stay busy instead of idling until the longest path of the warp
+//     finishes (the reference nests samples x bounces per work-item);
+//   * closest hit is a running minimum in registers (the reference zero-fills a 6.9 KB `context`
+//     per bounce and scans it afterwards, tracer.cl:886, 727-741) and shading is fused into the
+//     segment loop (the reference stores bounces and replays them, 1071-1096 -> 1116-1179);
+//   * the <=16 scene objects live in shared memory as compact affine records read with broadcast
+//     loads (the reference copies 16 KB of 1024-byte records per work-item, tracer.cl:846-849);
+//   * the BVH is re-emitted in traversal (pre-)order with skip links, so the walk needs no stack
+//     and visits exactly the nodes, in exactly the order, of the reference's stack walk
+//     (tracer.cl:624-714); nodes and triangles are 16-byte-vectorised records (48 B of test data
+//     per triangle instead of a 512-byte stride);
+//   * everything is templated on the arithmetic type: float = "fp32 mode", double = tracer.cl.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rng.cuh"
+
+namespace ptk {
+
+constexpr int kMaxObjects = 16;
+constexpr int kBlockThreads = 128;
+constexpr int kTileW = 8, kTileH = 4;   // pixels covered by one warp
+
+template <typename R> struct alignas(16) V4 { R x, y, z, w; };
+template <typename R> struct V3 { R x, y, z; };
+
+// ---- scalar math, overloaded on the arithmetic type -------------------------------------------
+__device__ __forceinline__ float m_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double m_sqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float m_rsqrt(float a) { return rsqrtf(a); }
+__device__ __forceinline__ double m_rsqrt(double a) { return 1.0 / sqrt(a); }
+__device__ __forceinline__ float m_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double m_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float m_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double m_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float m_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double m_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ void m_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void m_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ float m_acos(float a) { return acosf(a); }
+__device__ __forceinline__ double m_acos(double a) { return acos(a); }
+__device__ __forceinline__ float m_atan2(float a, float b) { return atan2f(a, b); }
+__device__ __forceinline__ double m_atan2(double a, double b) { return atan2(a, b); }
+__device__ __forceinline__ float m_fmod(float a, float b) { return fmodf(a, b); }
+__device__ __forceinline__ double m_fmod(double a, double b) { return fmod(a, b); }
+__device__ __forceinline__ float m_round(float a) { return roundf(a); }
+__device__ __forceinline__ double m_round(double a) { return round(a); }
+template <typename R> __device__ __forceinline__ R m_huge();
+template <> __device__ __forceinline__ float m_huge<float>() { return __int_as_float(0x7f800000); }
+template <> __device__ __forceinline__ double m_huge<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+template <typename R> __device__ __forceinline__ V3<R> operator+(V3<R> a, V3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator-(V3<R> a, V3<R> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename R> __device__ __forceinline__ V3<R> operator*(V3<R> a, R s) { return {a.x * s, a.y * s, a.z * s}; }
+template <typename R> __device__ __forceinline__ V3<R> operator*(V3<R> a, V3<R> b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { return a * m_rsqrt(dot(a, a)); }
+
+// ---- device scene ------------------------------------------------------------------------------
+// One scene object, converted once on the host from the 1024-byte wire record (ptw_object).  All
+// transforms on the path are affine (bottom row 0,0,0,1; points keep w=1, directions w=0), so only
+// the top three rows of the inverse and the 3x3 of the inverse-transpose are kept.
+template <typename R> struct alignas(16) DObj {
+    R inv[12];          // rows 0..2 of `inverse`            (tracer.cl:547-548)
+    R invt[9];          // 3x3 of `inverseTranspose`         (tracer.cl:953)
+    R color[3];
+    R emission[3];
+    R bb_min[3];
+    R bb_max[3];
+    R refractive_index, reflectivity, min_y, max_y;
+    R tex_sx, tex_sy, tex_sx_nm, tex_sy_nm;
+    int type;           // 0 plane 1 sphere 2 cylinder 3 cube 4 group
+    int node_begin, node_end;   // group: range of BVH nodes (all root children, in root order)
+    int flags;          // bit0 textured, bit1 normal-mapped
+    int tex_index, tex_index_nm;
+    int pad0, pad1;
+};
+
+template <typename R> struct DCam {
+    R pixel_size, half_width, half_height, aperture, focal_length;
+    R inv[12];          // rows 0..2 of the camera inverse
+    int width, height;
+};
+
+struct DTex { const uchar4* data; int w, h, layers; };
+
+template <typename R> struct Params {
+    const DObj<R>* objects;     int n_objects;
+    const V4<R>* node_lo;       // (min.xyz, -)
+    const V4<R>* node_hi;       // (max.xyz, -)
+    const int4* node_meta;      // (tri_begin, tri_count, skip, -)
+    const V4<R>* tri_test;      // 3 per triangle: (p1.xyz,e1.x) (e1.yz,e2.xy) (e2.z,-,-,-)
+    const V4<R>* tri_shade;     // 3 per triangle: (n1.xyz,col.r) (n2.xyz,col.g) (n3.xyz,col.b)
+    DCam<R> cam;
+    DTex tex[3];
+    const double* seeds;        // full frame, row-major
+    const int* row_map;         // local row -> frame row
+    double* out;                // rows * width * 4 (RGBA), or per-slice partial sums when slices > 1
+    int rows;                   // local rows rendered by this device
+    int samples;
+    int slices;                 // sample slices per pixel (gridDim.y)
+    R pi;                       // (double)3.14159265359f, tracer.cl:1
+    R eps;                      // 0.0001, tracer.cl:4
+};
+
+// ---- texture fetch: OpenCL 1.2 sampler NORMALIZED | REPEAT | LINEAR on RGBA8 (tracer.cl:829) -----
+// Done by hand, unfused fp32 in the spec's order: CUDA's hardware filter interpolates with 8
+// fractional bits, which would cost ~2e-3 of accuracy against the OpenCL result.
+__device__ __forceinline__ float3 sample_rgba8(const DTex& t, float s, float tt, int layer) {
+    if (t.data == nullptr) return make_float3(0.f, 0.f, 0.f);
+    float u = __fmul_rn(__fsub_rn(s, floorf(s)), (float)t.w);
+    float v = __fmul_rn(__fsub_rn(tt, floorf(tt)), (float)t.h);
+    float um = __fsub_rn(u, 0.5f), vm = __fsub_rn(v, 0.5f);
+    float fu = floorf(um), fv = floorf(vm);
+    int i0 = (int)fu, j0 = (int)fv;
+    int i1 = i0 + 1, j1 = j0 + 1;
+    if (i0 < 0) i0 += t.w;
+    if (i1 > t.w - 1) i1 -= t.w;
+    if (j0 < 0) j0 += t.h;
+    if (j1 > t.h - 1) j1 -= t.h;
+    float a = __fsub_rn(um, fu), b = __fsub_rn(vm, fv);
+    layer = max(0, min(layer, t.layers - 1));
+    const uchar4* base = t.data + (size_t)layer * t.w * t.h;
+    uchar4 c00 = __ldg(base + (size_t)j0 * t.w + i0), c10 = __ldg(base + (size_t)j0 * t.w + i1);
+    uchar4 c01 = __ldg(base + (size_t)j1 * t.w + i0), c11 = __ldg(base + (size_t)j1 * t.w + i1);
+    float w00 = __fmul_rn(__fsub_rn(1.0f, a), __fsub_rn(1.0f, b)), w10 = __fmul_rn(a, __fsub_rn(1.0f, b));
+    float w01 = __fmul_rn(__fsub_rn(1.0f, a), b), w11 = __fmul_rn(a, b);
+    auto mix = [&](unsigned char p00, unsigned char p10, unsigned char p01, unsigned char p11) {
+        float r = __fmul_rn(w00, __fdiv_rn((float)p00, 255.0f));
+        r = __fadd_rn(r, __fmul_rn(w10, __fdiv_rn((float)p10, 255.0f)));
+        r = __fadd_rn(r, __fmul_rn(w01, __fdiv_rn((float)p01, 255.0f)));
+        r = __fadd_rn(r, __fmul_rn(w11, __fdiv_rn((float)p11, 255.0f)));
+        return r;
+    };
+    return make_float3(mix(c00.x, c10.x, c01.x, c11.x), mix(c00.y, c10.y, c01.y, c11.y), mix(c00.z, c10.z, c01.z, c11.z));
+}
+
+// 16/32-byte records through the read-only path
+__device__ __forceinline__ V4<float> ldg4(const V4<float>* p) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ V4<double> ldg4(const V4<double>* p) {
+    double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return {a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ float ldg1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ double ldg1(const double* p) { return __ldg(p); }
+
+// ---- geometry helpers ----------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ V3<R> xf_point(const R* m, V3<R> p) {   // rows 0..2, w = 1
+    return {m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+            m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]};
+}
+template <typename R> __device__ __forceinline__ V3<R> xf_dir(const R* m, V3<R> d) {     // rows 0..2, w = 0
+    return {m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z, m[8] * d.x + m[9] * d.y + m[10] * d.z};
+}
+
+// tracer.cl:250-268 checkAxis
+template <typename R> __device__ __forceinline__ void check_axis(R origin, R direction, R lo, R hi, R eps, R& tmin, R& tmax) {
+    R a = lo - origin, b = hi - origin;
+    R t0, t1;
+    if (m_abs(direction) >= eps) { t0 = a / direction; t1 = b / direction; }
+    else { t0 = a * m_huge<R>(); t1 = b * m_huge<R>(); }
+    bool sw = t0 > t1;
+    tmin = sw ? t1 : t0;
+    tmax = sw ? t0 : t1;
+}
+// tracer.cl:270-280 intersectRayWithBox
+template <typename R> __device__ __forceinline__ bool ray_box(V3<R> o, V3<R> d, R lx, R ly, R lz, R hx, R hy, R hz, R eps) {
+    R x0, x1, y0, y1, z0, z1;
+    check_axis(o.x, d.x, lx, hx, eps, x0, x1);
+    check_axis(o.y, d.y, ly, hy, eps, y0, y1);
+    check_axis(o.z, d.z, lz, hz, eps, z0, z1);
+    return m_max(m_max(x0, y0), z0) < m_min(m_min(x1, y1), z1);
+}
+
+// tracer.cl:485-505
+template <typename R> __device__ __forceinline__ R schlick(V3<R> eye, V3<R> n, R n1, R n2) {
+    R c = dot(eye, n);
+    if (n1 > n2) {
+        R r = n1 / n2;
+        R sin2 = (r * r) * (R(1) - c * c);
+        if (sin2 > R(1)) return R(1);
+        c = m_sqrt(R(1) - sin2);
+    }
+    R t = (n1 - n2) / (n1 + n2);
+    R r0 = t * t;
+    R k = R(1) - c;
+    R k2 = k * k;
+    return r0 + (R(1) - r0) * (k2 * k2 * k);
+}
+// tracer.cl:507-533
+template <typename R> __device__ __forceinline__ V3<R> refracted(V3<R> eye, V3<R> n, R n1, R n2) {
+    R ratio = n1 / n2;
+    R cos_i = dot(eye, n);
+    R sin2 = (ratio * ratio) * (R(1) - cos_i * cos_i);
+    if (sin2 > R(1)) return {R(0), R(0), R(0)};
+    R cos_t = m_sqrt(R(1) - sin2);
+    return n * (ratio * cos_i - cos_t) - eye * ratio;
+}
+
+// tracer.cl:113-175, constants as written there
+template <typename R> __device__ __forceinline__ void cube_uv(V3<R> p, R& ou, R& ov) {
+    R coord = m_max(m_max(m_abs(p.x), m_abs(p.y)), m_abs(p.z));
+    const R third = R(0.333333), two3 = R(0.6666666);
+    R u, v;
+    if (coord == p.x) { u = m_fmod(R(1) - p.z, R(2)) / R(2); v = m_fmod(p.y + R(1), R(2)) / R(2); ou = R(0.5) + u * R(0.25); ov = two3 - v * third; }
+    else if (coord == -p.x) { u = m_fmod(p.z + R(1), R(2)) / R(2); v = m_fmod(p.y + R(1), R(2)) / R(2); ou = u * R(0.25); ov = two3 - v * third; }
+    else if (coord == p.y) { u = m_fmod(p.x + R(1), R(2)) / R(2); v = m_fmod(R(1) - p.z, R(2)) / R(2); ou = R(0.25) + u * R(0.25); ov = R(1) - v * third; }
+    else if (coord == -p.y) { u = m_fmod(p.x + R(1), R(2)) / R(2); v = m_fmod(p.z + R(1), R(2)) / R(2); ou = R(0.25) + u * R(0.25); ov = v * third; }
+    else if (coord == p.z) { u = m_fmod(p.x + R(1), R(2)) / R(2); v = m_fmod(p.y + R(1), R(2)) / R(2); ou = R(0.25) + u * R(0.25); ov = two3 - v * third; }
+    else { u = m_fmod(R(1) - p.x, R(2)) / R(2); v = m_fmod(p.y + R(1), R(2)) / R(2); ou = R(0.75) + u * R(0.25); ov = two3 - v * third; }
+}
+
+// Closest-hit record kept in registers while scanning the scene.
+template <typename R> struct Hit {
+    R t;        // running minimum, starts at 1024 (tracer.cl:728)
+    int obj;    // -1 = none
+    int tri;    // winning triangle (groups)
+    R u, v;     // its barycentrics (normal interpolation, tracer.cl:669)
+};
+
+// A candidate wins iff EPS < t < current best: strict '<' keeps the first-recorded hit on ties,
+// the reference's selection rule (tracer.cl:731-739).  NaN fails both comparisons.
+template <typename R> __device__ __forceinline__ void offer(Hit<R>& h, R t, int obj, R eps) {
+    if (t > eps && t < h.t) { h.t = t; h.obj = obj; }
+}
+
+// Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.
+template <typename R>
+__device__ __forceinline__ void closest_hit(const Params<R>& P, const DObj<R>* __restrict__ objs, V3<R> ro, V3<R> rd, Hit<R>& h) {
+    const R eps = P.eps;
+    h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
+    for (int j = 0; j < P.n_objects; ++j) {
+        const DObj<R>& ob = objs[j];
+        const int type = ob.type;
+        if (type == 0) {                                         // plane, tracer.cl:478-483
+            R oy = ob.inv[4] * ro.x + ob.inv[5] * ro.y + ob.inv[6] * ro.z + ob.inv[7];
+            R dy = ob.inv[4] * rd.x + ob.inv[5] * rd.y + ob.inv[6] * rd.z;
+            if (m_abs(dy) > eps) offer(h, -oy / dy, j, eps);
+        } else if (type == 1) {                                  // sphere, tracer.cl:448-476
+            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+            R a = dot(d, d);
+            R b = R(2) * dot(d, o);
+            R c = dot(o, o) - R(1);
+            R disc = b * b - R(4) * a * c;
+            if (disc > R(0)) {
+                R sq = m_sqrt(disc), den = R(2) * a;
+                offer(h, (-b - sq) / den, j, eps);
+                offer(h, (-b + sq) / den, j, eps);
+            }
+        } else if (type == 2) {                                  // cylinder side, caps off, tracer.cl:396-446
+            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+            R a = d.x * d.x + d.z * d.z;
+            if (!(m_abs(a) < eps)) {
+                R b = R(2) * o.x * d.x + R(2) * o.z * d.z;
+                R c = o.x * o.x + o.z * o.z - R(1);
+                R disc = b * b - R(4) * a * c;
+                if (!(disc < R(0))) {
+                    R sq = m_sqrt(disc), den = R(2) * a;
+                    R t0 = (-b - sq) / den, t1 = (-b + sq) / den;
+                    R y0 = o.y + t0 * d.y, y1 = o.y + t1 * d.y;
+                    if (y0 > ob.min_y && y0 < ob.max_y) offer(h, t0, j, eps);
+                    if (y1 > ob.min_y && y1 < ob.max_y) offer(h, t1, j, eps);
+                }
+            }
+        } else if (type == 3) {                                  // cube, tracer.cl:378-394
+            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+            R x0, x1, y0, y1, z0, z1;
+            check_axis(o.x, d.x, R(-1), R(1), eps, x0, x1);
+            check_axis(o.y, d.y, R(-1), R(1), eps, y0, y1);
+            check_axis(o.z, d.z, R(-1), R(1), eps, z0, z1);
+            R tmin = m_max(m_max(x0, y0), z0), tmax = m_min(m_min(x1, y1), z1);
+            if (!(tmin > tmax)) { offer(h, tmin, j, eps); offer(h, tmax, j, eps); }
+        } else if (type == 4) {                                  // group: AABB, then BVH, tracer.cl:598-720
+            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+            if (!ray_box(o, d, ob.bb_min[0], ob.bb_min[1], ob.bb_min[2], ob.bb_max[0], ob.bb_max[1], ob.bb_max[2], eps)) continue;
+            int i = ob.node_begin;
+            const int end = ob.node_end;
+            while (i < end) {
+                const V4<R> lo = ldg4(&P.node_lo[i]), hi = ldg4(&P.node_hi[i]);
+                const int4 meta = __ldg(&P.node_meta[i]);
+                if (!ray_box(o, d, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, eps)) { i = meta.z; continue; }
+                const int tend = meta.x + meta.y;
+                for (int n = meta.x; n < tend; ++n) {            // Moeller-Trumbore, tracer.cl:640-675
+                    const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
+                    const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * n + 2].x)};
+                    const V3<R> e1 = {q0.w, q1.x, q1.y};
+                    V3<R> dxe2 = cross(d, e2);
+                    R det = dot(e1, dxe2);
+                    if (m_abs(det) < eps) continue;
+                    R f = R(1) / det;
+                    V3<R> s = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
+                    R u = f * dot(s, dxe2);
+                    if (u < R(0) || u > R(1)) continue;
+                    V3<R> sxe1 = cross(s, e1);
+                    R v = f * dot(d, sxe1);
+                    if (v < R(0) || (u + v) > R(1)) continue;
+                    R t = f * dot(e2, sxe1);
+                    if (t > eps && t < h.t) { h.t = t; h.obj = j; h.tri = n; h.u = u; h.v = v; }
+                }
+                i = i + 1;
+            }
+        }
+    }
+}
+
+// tracer.cl:221-248 sunflower(amountPoints, alpha=2, pointNumber, randomize=false)
+template <typename R> __device__ __forceinline__ void sunflower(int amount, int index, R pi, R& ox, R& oy) {
+    R idx = R(index), n = R(amount);
+    R b = m_round(R(2) * m_sqrt(n));
+    R phi = (m_sqrt(R(5)) + R(1)) / R(2);
+    R r = R(1);
+    if (idx <= (n - b)) r = m_sqrt(idx - R(0.5)) / m_sqrt(n - (b + R(1)) / R(2));   // NaN at index 0: kept
+    R theta = R(2) * pi * idx / (phi * phi);
+    R s, c;
+    m_sincos(theta, &s, &c);
+    ox = r * c;
+    oy = r * s;
+}
+
+template <typename R, int RNG>
+__global__ void __launch_bounds__(kBlockThreads) trace_kernel(const __grid_constant__ Params<R> P) {
+    __shared__ DObj<R> s_obj[kMaxObjects];
+    {   // stage the object records once per block (tracer.cl:846-849 does it per work-item)
+        const int words = P.n_objects * (int)(sizeof(DObj<R>) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.objects);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_obj);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const int W = P.cam.width;
+    const int tiles_x = (W + kTileW - 1) / kTileW;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int lx = (warp % tiles_x) * kTileW + (lane & (kTileW - 1));
+    const int ly = (warp / tiles_x) * kTileH + (lane / kTileW);
+    if (lx >= W || ly >= P.rows) return;
+    const int gy = P.row_map[ly];
+    const int slice = blockIdx.y;
+
+    const R eps = P.eps, pi = P.pi;
+    const unsigned samples = (unsigned)P.samples;
+    const double seed = P.seeds[(size_t)gy * W + lx];
+    const float fgi = (float)(seed / (double)P.n_objects);     // tracer.cl:840
+    const float fgi2 = (float)(seed / (double)samples);        // tracer.cl:841
+
+    const R px = R(lx), py = R(gy);
+    const V3<R> cam_origin = {P.cam.inv[3], P.cam.inv[7], P.cam.inv[11]};   // inverse * (0,0,0,1)
+
+    double col_r = 0.0, col_g = 0.0, col_b = 0.0;
+
+    // per-path state
+    unsigned n = (unsigned)slice;      // sample index (tracer.cl:867)
+    unsigned b = 0, effective = 0;     // bounce counters (tracer.cl:873-884)
+    bool inside = false;
+    bool fresh = true;                 // need a new camera ray
+    V3<R> ro = {R(0), R(0), R(0)}, rd = {R(0), R(0), R(0)};
+    V3<R> mask = {R(1), R(1), R(1)}, accum = {R(0), R(0), R(0)};
+
+    while (true) {
+        if (fresh) {
+            if (n >= samples) break;
+            // rayForPixel, tracer.cl:745-779
+            float jx = noise3d<RNG>(fgi, (float)n, fgi2);
+            float jy = noise3d<RNG>(fgi, fgi2, (float)n);
+            R xo = P.cam.pixel_size * (px + R(jx));
+            R yo = P.cam.pixel_size * (py + R(jy));
+            V3<R> in_view = {P.cam.half_width - xo, P.cam.half_height - yo, R(-1)};
+            V3<R> pixel = xf_point(P.cam.inv, in_view);
+            ro = cam_origin;
+            rd = normalize(pixel - ro);
+            if (P.cam.aperture != R(0)) {
+                V3<R> pos = ro + rd * P.cam.focal_length;
+                R sx, sy;
+                sunflower<R>((int)samples, (int)n, pi, sx, sy);
+                V3<R> no = {ro.x + sy * P.cam.aperture, ro.y + sx * P.cam.aperture, ro.z};   // x/y swap as upstream
+                rd = pos - no;                                                                // left unnormalised
+                ro = no;
+            }
+            b = 0; effective = 0; inside = false;
+            mask = {R(1), R(1), R(1)}; accum = {R(0), R(0), R(0)};
+            fresh = false;
+        }
+
+        Hit<R> h;
+        closest_hit<R>(P, s_obj, ro, rd, h);
+
+        bool done = true;                        // a miss ends the path (re-tracing it cannot hit either)
+        if (h.obj >= 0) {
+            const DObj<R>& ob = s_obj[h.obj];
+            const int type = ob.type;
+            V3<R> position = ro + rd * h.t;
+            V3<R> eye = {-rd.x, -rd.y, -rd.z};
+            V3<R> lp = {R(0), R(0), R(0)};
+            if (type != 4) lp = xf_point(ob.inv, position);
+            V3<R> on;
+            V3<R> tri_color = {R(0), R(0), R(0)};
+            if (type == 0) {                                                      // tracer.cl:906-914
+                if (ob.flags & 2) {
+                    float3 c = sample_rgba8(P.tex[0], (float)(m_abs(lp.x) * ob.tex_sx_nm), (float)(m_abs(lp.z) * ob.tex_sy_nm), ob.tex_index_nm);
+                    on = normalize(V3<R>{R(c.x), R(c.y), R(c.z)});
+                } else on = {R(0), R(1), R(0)};
+            } else if (type == 1) {
+                on = lp;                                                          // tracer.cl:919-920
+            } else if (type == 2) {                                               // tracer.cl:924-932
+                R dist = lp.x * lp.x + lp.z * lp.z;
+                if (dist < R(1) && lp.y >= ob.max_y - eps) on = {R(0), R(1), R(0)};
+                else if (dist < R(1) && lp.y <= ob.min_y + eps) on = {R(0), R(-1), R(0)};
+                else on = {lp.x, R(0), lp.z};
+            } else if (type == 3) {                                               // tracer.cl:938-946
+                R ax = m_abs(lp.x), ay = m_abs(lp.y), az = m_abs(lp.z);
+                R maxc = m_max(m_max(ax, ay), az);
+                if (maxc == ax) on = {lp.x, R(0), R(0)};
+                else if (maxc == ay) on = {R(0), lp.y, R(0)};
+                else on = {R(0), R(0), lp.z};
+            } else {                                                              // tracer.cl:669, 949
+                const V4<R> s0 = ldg4(&P.tri_shade[3 * h.tri]), s1 = ldg4(&P.tri_shade[3 * h.tri + 1]), s2 = ldg4(&P.tri_shade[3 * h.tri + 2]);
+                R w = R(1) - h.u - h.v;
+                on = {s1.x * h.u + s2.x * h.v + s0.x * w, s1.y * h.u + s2.y * h.v + s0.y * w, s1.z * h.u + s2.z * h.v + s0.z * w};
+                tri_color = {s0.w, s1.w, s2.w};
+            }
+            V3<R> nv = {ob.invt[0] * on.x + ob.invt[1] * on.y + ob.invt[2] * on.z,
+                        ob.invt[3] * on.x + ob.invt[4] * on.y + ob.invt[5] * on.z,
+                        ob.invt[6] * on.x + ob.invt[7] * on.y + ob.invt[8] * on.z};     // tracer.cl:953-955
+            nv = normalize(nv);
+            if (dot(eye, nv) < R(0)) nv = nv * R(-1);                                  // tracer.cl:962-964
+            V3<R> over = position + nv * eps;
+            const V3<R> under = position - nv * eps;
+
+            // material branch, tracer.cl:975-1062
+            R cosine = R(1);
+            bool entering = false, exiting = false, reflecting = false;
+            const R refl = ob.reflectivity, ri = ob.refractive_index;
+            bool mirror = false;
+            if (refl != R(0) && R(noise3d<RNG>(fgi, (float)n, (float)b)) < refl) {
+                mirror = true;
+            } else if (ri == R(-1)) {                                                 // thin glass
+                if (schlick(eye, nv, R(1), R(1.5)) < R(noise3d<RNG>(fgi, (float)(n * n), (float)b))) over = under;
+                else mirror = true;
+            } else if (ri != R(1)) {
+                R rnd = R(noise3d<RNG>(fgi, (float)(n * n), (float)b));
+                if (!inside) {
+                    if (schlick(eye, nv, R(1), ri) < rnd) { rd = refracted(eye, nv, R(1), ri); over = under; inside = true; entering = true; }
+                    else mirror = true;
+                } else {
+                    if (schlick(eye, nv, ri, R(1)) < rnd) { rd = refracted(eye, nv, ri, R(1)); over = under; inside = false; exiting = true; }
+                    else mirror = true;
+                }
+            } else {                                                                  // diffuse, tracer.cl:348-366
+                R rand1 = R(2) * pi * R(noise3d<RNG>(fgi, (float)b, (float)n));
+                R rand2 = R(noise3d<RNG>((float)b, (float)n, fgi));
+                R rand2s = m_sqrt(rand2);
+                V3<R> axis = (m_abs(nv.x) > R(0.1)) ? V3<R>{R(0), R(1), R(0)} : V3<R>{R(1), R(0), R(0)};
+                V3<R> uu = normalize(cross(axis, nv));
+                V3<R> vv = cross(nv, uu);
+                R s1, c1;
+                m_sincos(rand1, &s1, &c1);
+                rd = uu * (c1 * rand2s) + vv * (s1 * rand2s) + nv * m_sqrt(R(1) - rand2);
+                cosine = dot(rd, nv);
+            }
+            if (mirror) {                                                             // tracer.cl:985-988
+                R ds = dot(rd, nv);
+                rd = rd - nv * (R(2) * ds);
+                reflecting = true;
+            }
+            ro = over;
+
+            // surface colour, tracer.cl:1071-1096
+            V3<R> colr, emis;
+            if (type == 4) { colr = tri_color; emis = {R(0), R(0), R(0)}; }
+            else {
+                colr = {ob.color[0], ob.color[1], ob.color[2]};
+                emis = {ob.emission[0], ob.emission[1], ob.emission[2]};
+                if (ob.flags & 1) {
+                    if (type == 0) {
+                        float3 c = sample_rgba8(P.tex[0], (float)(lp.x * ob.tex_sx), (float)(lp.z * ob.tex_sy), ob.tex_index);
+                        colr = {R(c.x), R(c.y), R(c.z)};
+                    } else if (type == 1) {                                           // sphericalMap, tracer.cl:178-213
+                        R theta = m_atan2(lp.x, lp.z);
+                        R radius = m_sqrt(dot(lp, lp));
+                        R phi = m_acos(lp.y / radius);
+                        R su = R(1) - (theta / (R(2) * pi) + R(0.5));
+                        R sv = R(1) - phi / pi;
+                        float3 c = sample_rgba8(P.tex[1], (float)su, (float)(R(1) - sv), ob.tex_index);
+                        colr = {R(c.x), R(c.y), R(c.z)};
+                    } else if (type == 3) {
+                        R cu, cv;
+                        cube_uv(lp, cu, cv);
+                        float3 c = sample_rgba8(P.tex[2], (float)cu, (float)cv, ob.tex_index);
+                        colr = {R(c.x), R(c.y), R(c.z)};
+                    }
+                }
+            }
+
+            // fused shading, tracer.cl:1116-1176: refraction bounces are skipped; an emitter adds
+            // mask*emission (or, when hit directly by the camera ray, replaces accum by its colour)
+            if (!(entering || exiting)) {
+                accum = accum + mask * emis;
+                if (emis.x > R(0)) { if (b == 0) accum = colr; }
+                mask = mask * colr;
+                mask = mask * cosine;
+            }
+            if (!entering && !exiting && !reflecting) effective++;                    // tracer.cl:1099-1101
+            b++;
+            done = (ob.emission[0] > R(0)) || !(b < 10u && effective < 4u);           // tracer.cl:1107, 884
+        }
+        if (done) {
+            col_r += (double)accum.x; col_g += (double)accum.y; col_b += (double)accum.z;   // tracer.cl:1179
+            n += (unsigned)P.slices;
+            fresh = true;
+        }
+    }
+
+    const size_t pix = (size_t)ly * W + lx;
+    if (P.slices == 1) {
+        const double wgt = 1.0 / (double)samples;                                    // tracer.cl:837, 1184-1187
+        double4* o = reinterpret_cast<double4*>(P.out) + pix;
+        *o = make_double4(col_r * wgt, col_g * wgt, col_b * wgt, 1.0);
+    } else {
+        double4* o = reinterpret_cast<double4*>(P.out) + ((size_t)slice * P.rows * W + pix);
+        *o = make_double4(col_r, col_g, col_b, 0.0);
+    }
+}
+
+// Sums the per-slice partials in slice order (deterministic) and applies the 1/samples weight.
+__global__ void resolve_slices_kernel(const double4* __restrict__ partial, double4* __restrict__ out, int pixels, int slices, int samples) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    double r = 0.0, g = 0.0, b = 0.0;
+    for (int s = 0; s < slices; ++s) {
+        double4 p = partial[(size_t)s * pixels + i];
+        r += p.x; g += p.y; b += p.z;
+    }
+    const double wgt = 1.0 / (double)samples;
+    out[i] = make_double4(r * wgt, g * wgt, b * wgt, 1.0);
+}
+
+// Test hook: evaluate the RNG on the device (parity tests compare it bit for bit with the oracle).
+__global__ void noise3d_kernel(const float* __restrict__ xyz, float* __restrict__ out, int n, int mode) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    out[i] = mode == RNG_PARITY ? noise3d<RNG_PARITY>(x, y, z) : noise3d<RNG_FAST>(x, y, z);
+}
+
+}  // namespace ptk

@@ -1,0 +1,563 @@
+// ptcuda.cu -- libptcuda: C ABI (include/ptcuda.h) + host driver for the sm_100a path tracer.
+//
+// Replaces the host side of the reference's OpenCL path (reference internal/ocl/ocltracer.go):
+//   Trace()            :100-226  -> ptc_open + ptc_trace + ptc_read (ptc_render does all three)
+//   prepareTextures()  :228-254  -> upload_textures()
+//   computeBatch()     :256-376  -> one launch per device for the whole frame instead of H/4
+//                                   create/upload/launch/finish/readback rounds
+// and cmd/pt/main.go:98-112 listDevices() -> ptc_device_count / ptc_device_name.
+// There is no CPU path in this library: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ptcuda.h"
+#include "../../include/ptwire.h"
+#include "kernels/trace.cuh"
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+struct Error : std::exception {
+    std::string msg;
+    explicit Error(std::string m) : msg(std::move(m)) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+[[noreturn]] void fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(buf);
+}
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+void set_err(char* err, int errlen, const char* msg) {
+    if (err && errlen > 0) std::snprintf(err, size_t(errlen), "%s", msg);
+}
+
+// ---- flattened scene (host copy), templated on the arithmetic type -----------------------------
+template <typename R> struct HostScene {
+    std::vector<ptk::DObj<R>> objects;
+    std::vector<ptk::V4<R>> node_lo, node_hi;
+    std::vector<int4> node_meta;
+    std::vector<ptk::V4<R>> tri_test, tri_shade;
+    ptk::DCam<R> cam;
+};
+
+// Re-emit the BVH below every root child of a group object in traversal order: node, then the
+// subtree of children[0], then the subtree of children[1] -- the visiting order of the reference's
+// stack walk (tracer.cl:624-714; "children[k] > 0" means "has child", scene.go:139-152).  Each
+// node's triangles are appended contiguously as it is emitted, and `skip` points past its subtree.
+template <typename R>
+void emit_subtree(const ptw_group* groups, int n_groups, const ptw_triangle* tris, int n_tris, int g, int depth, HostScene<R>& out) {
+    if (g < 0 || g >= n_groups) fail("BVH node index %d out of range (%d groups)", g, n_groups);
+    if (depth > PTW_BVH_STACK) fail("BVH deeper than %d levels (the reference's traversal stack, tracer.cl:624)", PTW_BVH_STACK);
+    const ptw_group& s = groups[g];
+    const int me = int(out.node_lo.size());
+    out.node_lo.push_back({R(s.bb_min[0]), R(s.bb_min[1]), R(s.bb_min[2]), R(0)});
+    out.node_hi.push_back({R(s.bb_max[0]), R(s.bb_max[1]), R(s.bb_max[2]), R(0)});
+    int4 meta;
+    meta.x = int(out.tri_test.size() / 3);
+    meta.y = s.tri_count > 0 ? s.tri_count : 0;
+    meta.z = 0; meta.w = 0;
+    if (meta.y > 0 && (s.tri_offset < 0 || s.tri_offset + s.tri_count > n_tris)) fail("BVH node %d references triangles outside the buffer", g);
+    for (int k = 0; k < meta.y; ++k) {
+        const ptw_triangle& t = tris[s.tri_offset + k];
+        out.tri_test.push_back({R(t.p1[0]), R(t.p1[1]), R(t.p1[2]), R(t.e1[0])});
+        out.tri_test.push_back({R(t.e1[1]), R(t.e1[2]), R(t.e2[0]), R(t.e2[1])});
+        out.tri_test.push_back({R(t.e2[2]), R(0), R(0), R(0)});
+        out.tri_shade.push_back({R(t.n1[0]), R(t.n1[1]), R(t.n1[2]), R(t.color[0])});
+        out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
+        out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
+    }
+    out.node_meta.push_back(meta);
+    if (s.children[0] > 0) emit_subtree(groups, n_groups, tris, n_tris, s.children[0], depth + 1, out);
+    if (s.children[1] > 0) emit_subtree(groups, n_groups, tris, n_tris, s.children[1], depth + 1, out);
+    out.node_meta[size_t(me)].z = int(out.node_lo.size());
+}
+
+template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
+    const auto* objs = static_cast<const ptw_object*>(job.objects);
+    const auto* tris = static_cast<const ptw_triangle*>(job.triangles);
+    const auto* groups = static_cast<const ptw_group*>(job.groups);
+    for (int i = 0; i < job.n_objects; ++i) {
+        const ptw_object& s = objs[i];
+        ptk::DObj<R> o;
+        std::memset(&o, 0, sizeof o);
+        for (int k = 0; k < 12; ++k) o.inv[k] = R(s.inverse[k]);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) o.invt[r * 3 + c] = R(s.inverse_transpose[r * 4 + c]);
+        for (int k = 0; k < 3; ++k) {
+            o.color[k] = R(s.color[k]); o.emission[k] = R(s.emission[k]);
+            o.bb_min[k] = R(s.bb_min[k]); o.bb_max[k] = R(s.bb_max[k]);
+        }
+        o.refractive_index = R(s.refractive_index); o.reflectivity = R(s.reflectivity);
+        o.min_y = R(s.min_y); o.max_y = R(s.max_y);
+        o.tex_sx = R(s.texture_scale_x); o.tex_sy = R(s.texture_scale_y);
+        o.tex_sx_nm = R(s.texture_scale_x_nm); o.tex_sy_nm = R(s.texture_scale_y_nm);
+        o.type = (s.type >= 0 && s.type <= 4) ? int(s.type) : 999;
+        o.flags = (s.is_textured ? 1 : 0) | (s.is_textured_nm ? 2 : 0);
+        o.tex_index = s.texture_index; o.tex_index_nm = s.texture_index_nm;
+        o.node_begin = o.node_end = int(out.node_lo.size());
+        if (o.type == 4 && s.child_count > 0) {
+            if (s.child_count > PTW_MAX_ROOT_CHILDREN) fail("object %d: child_count %d > %d", i, s.child_count, PTW_MAX_ROOT_CHILDREN);
+            if (!groups || job.n_groups <= 0) fail("object %d is a group but no BVH groups were passed", i);
+            for (int c = 0; c < s.child_count; ++c) emit_subtree<R>(groups, job.n_groups, tris, job.n_triangles, s.children[c], 0, out);
+            o.node_end = int(out.node_lo.size());
+        }
+        out.objects.push_back(o);
+    }
+    const auto* cam = static_cast<const ptw_camera*>(job.camera);
+    out.cam.pixel_size = R(cam->pixel_size); out.cam.half_width = R(cam->half_width); out.cam.half_height = R(cam->half_height);
+    out.cam.aperture = R(cam->aperture); out.cam.focal_length = R(cam->focal_length);
+    for (int k = 0; k < 12; ++k) out.cam.inv[k] = R(cam->inverse[k]);
+    out.cam.width = cam->width; out.cam.height = cam->height;
+}
+
+struct DeviceState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<int> rows;          // frame rows owned by this device, increasing
+    std::vector<void*> allocs;      // everything cudaMalloc'ed on this device
+    void* objects = nullptr; void* node_lo = nullptr; void* node_hi = nullptr; void* node_meta = nullptr;
+    void* tri_test = nullptr; void* tri_shade = nullptr;
+    void* tex[3] = {nullptr, nullptr, nullptr};
+    double* seeds = nullptr;
+    int* row_map = nullptr;
+    double* out = nullptr;          // rows*W*4
+    double* partial = nullptr;      // slices*rows*W*4 when slices > 1
+    int slices = 1;
+    int sm_count = 0;
+    float last_ms = 0.f;
+};
+
+}  // namespace
+
+struct ptc_context {
+    int width = 0, height = 0, samples = 0, precision = PTC_FP32, rng_mode = PTC_RNG_PARITY;
+    int n_objects = 0;
+    int shard_index = 0, shard_count = 1, rows_per_tile = 4;
+    std::vector<int> rows;                       // rows owned by this context (all its devices), increasing
+    std::vector<DeviceState> dev;
+    HostScene<float> scene32;
+    HostScene<double> scene64;
+    int tex_w[3] = {0, 0, 0}, tex_h[3] = {0, 0, 0}, tex_layers[3] = {0, 0, 0};
+    double* gather = nullptr;                    // on dev[0]: packed rows of the whole context (n_devices > 1)
+    bool peer_ok = false;
+    ptc_stats stats{};
+};
+
+namespace {
+
+void* dmalloc(DeviceState& d, size_t bytes) {
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, bytes ? bytes : 16));
+    d.allocs.push_back(p);
+    return p;
+}
+template <typename T> void* upload(DeviceState& d, const std::vector<T>& v, int64_t& h2d) {
+    void* p = dmalloc(d, v.size() * sizeof(T));
+    if (!v.empty()) {
+        CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, d.stream));
+        h2d += int64_t(v.size() * sizeof(T));
+    }
+    return p;
+}
+
+template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const HostScene<R>& s, int64_t& h2d) {
+    d.objects = upload(d, s.objects, h2d);
+    d.node_lo = upload(d, s.node_lo, h2d);
+    d.node_hi = upload(d, s.node_hi, h2d);
+    d.node_meta = upload(d, s.node_meta, h2d);
+    d.tri_test = upload(d, s.tri_test, h2d);
+    d.tri_shade = upload(d, s.tri_shade, h2d);
+    (void)c;
+}
+
+template <typename R> ptk::Params<R> make_params(const ptc_context& c, const DeviceState& d, const HostScene<R>& s) {
+    ptk::Params<R> P;
+    std::memset(&P, 0, sizeof P);
+    P.objects = static_cast<const ptk::DObj<R>*>(d.objects);
+    P.n_objects = c.n_objects;
+    P.node_lo = static_cast<const ptk::V4<R>*>(d.node_lo);
+    P.node_hi = static_cast<const ptk::V4<R>*>(d.node_hi);
+    P.node_meta = static_cast<const int4*>(d.node_meta);
+    P.tri_test = static_cast<const ptk::V4<R>*>(d.tri_test);
+    P.tri_shade = static_cast<const ptk::V4<R>*>(d.tri_shade);
+    P.cam = s.cam;
+    for (int k = 0; k < 3; ++k) P.tex[k] = ptk::DTex{static_cast<const uchar4*>(d.tex[k]), c.tex_w[k], c.tex_h[k], c.tex_layers[k]};
+    P.seeds = d.seeds;
+    P.row_map = d.row_map;
+    P.out = d.slices > 1 ? d.partial : d.out;
+    P.rows = int(d.rows.size());
+    P.samples = c.samples;
+    P.slices = d.slices;
+    P.pi = R(double(3.14159265359f));
+    P.eps = R(0.0001);
+    return P;
+}
+
+template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScene<R>& s) {
+    const int rows = int(d.rows.size());
+    if (rows == 0) return;
+    ptk::Params<R> P = make_params<R>(c, d, s);
+    const int tiles_x = (c.width + ptk::kTileW - 1) / ptk::kTileW;
+    const int tiles_y = (rows + ptk::kTileH - 1) / ptk::kTileH;
+    const long long warps = (long long)tiles_x * tiles_y;
+    const int warps_per_block = ptk::kBlockThreads / 32;
+    dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
+    dim3 block(ptk::kBlockThreads, 1, 1);
+    if (c.rng_mode == PTC_RNG_FAST) ptk::trace_kernel<R, ptk::RNG_FAST><<<grid, block, 0, d.stream>>>(P);
+    else ptk::trace_kernel<R, ptk::RNG_PARITY><<<grid, block, 0, d.stream>>>(P);
+    CUDA_OK(cudaGetLastError());
+    c.stats.kernel_launches++;
+    if (d.slices > 1) {
+        const int pixels = rows * c.width;
+        ptk::resolve_slices_kernel<<<(pixels + 255) / 256, 256, 0, d.stream>>>(reinterpret_cast<const double4*>(d.partial),
+                                                                            reinterpret_cast<double4*>(d.out), pixels, d.slices, c.samples);
+        CUDA_OK(cudaGetLastError());
+        c.stats.kernel_launches++;
+    }
+}
+
+void validate(const ptc_job& j) {
+    if (j.abi_version != PTC_ABI_VERSION) fail("ptc_job.abi_version %d != %d", j.abi_version, PTC_ABI_VERSION);
+    if (!j.objects || j.n_objects < 1) fail("scene has no objects");
+    if (j.n_objects > PTW_MAX_OBJECTS) fail("%d objects: the kernel supports at most %d (tracer.cl:846)", j.n_objects, PTW_MAX_OBJECTS);
+    if (!j.camera) fail("camera is NULL");
+    if (j.n_triangles < 0 || j.n_groups < 0) fail("negative triangle/group count");
+    if (j.n_triangles > 0 && !j.triangles) fail("n_triangles > 0 but triangles is NULL");
+    if (j.n_groups > 0 && !j.groups) fail("n_groups > 0 but groups is NULL");
+    const auto* cam = static_cast<const ptw_camera*>(j.camera);
+    if (cam->width <= 0 || cam->height <= 0) fail("camera %dx%d: width and height must be positive", cam->width, cam->height);
+    if ((long long)cam->width * cam->height > (1ll << 30)) fail("frame too large");
+    if (j.samples < 1) fail("samples must be >= 1");
+    if (!j.seeds) fail("seeds is NULL (one double per pixel)");
+    if (j.precision != PTC_FP32 && j.precision != PTC_FP64) fail("unknown precision %d", j.precision);
+    if (j.rng_mode != PTC_RNG_PARITY && j.rng_mode != PTC_RNG_FAST) fail("unknown rng_mode %d", j.rng_mode);
+    for (int k = 0; k < 3; ++k)
+        if (j.tex[k] && (j.tex_w[k] <= 0 || j.tex_h[k] <= 0 || j.tex_layers[k] <= 0)) fail("texture class %d has a non-positive size", k);
+    if (j.shard_count > 1 && (j.shard_index < 0 || j.shard_index >= j.shard_count)) fail("shard_index %d outside [0,%d)", j.shard_index, j.shard_count);
+    if (j.n_devices < 0 || (j.n_devices > 0 && !j.devices)) fail("bad device list");
+    for (int k = 0; k < 8; ++k) if (j.reserved[k] != 0) fail("ptc_job.reserved must be zero");
+}
+
+void destroy(ptc_context* c) {
+    if (!c) return;
+    for (DeviceState& d : c->dev) {
+        cudaSetDevice(d.device);
+        for (void* p : d.allocs) cudaFree(p);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete c;
+}
+
+ptc_context* open_impl(const ptc_job& job) {
+    validate(job);
+    auto t0 = Clock::now();
+    int n_cuda = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_cuda);
+    if (e != cudaSuccess || n_cuda <= 0)
+        fail("no usable CUDA device (%s); libptcuda has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+
+    std::unique_ptr<ptc_context, void (*)(ptc_context*)> guard(new ptc_context, destroy);
+    ptc_context& c = *guard;
+    const auto* cam = static_cast<const ptw_camera*>(job.camera);
+    c.width = cam->width; c.height = cam->height; c.samples = job.samples;
+    c.precision = job.precision; c.rng_mode = job.rng_mode; c.n_objects = job.n_objects;
+    c.shard_count = job.shard_count > 1 ? job.shard_count : 1;
+    c.shard_index = job.shard_count > 1 ? job.shard_index : 0;
+    c.rows_per_tile = job.rows_per_tile > 0 ? job.rows_per_tile : 4;
+    for (int k = 0; k < 3; ++k)
+        if (job.tex[k]) { c.tex_w[k] = job.tex_w[k]; c.tex_h[k] = job.tex_h[k]; c.tex_layers[k] = job.tex_layers[k]; }
+
+    std::vector<int> devices;
+    if (job.n_devices > 0) devices.assign(job.devices, job.devices + job.n_devices);
+    else devices.push_back(0);
+    for (size_t i = 0; i < devices.size(); ++i) {
+        // the reference maps a negative --device-index to 0 and aborts on an index past the end (ocltracer.go:135-141)
+        if (devices[i] < 0) devices[i] = 0;
+        if (devices[i] > n_cuda - 1) fail("device index %d out of bounds: highest device index: %d", devices[i], n_cuda - 1);
+        for (size_t k = 0; k < i; ++k) if (devices[k] == devices[i]) fail("device %d listed twice", devices[i]);
+    }
+    const int nd = int(devices.size());
+
+    // Row ownership: scanline tile k (rows_per_tile rows) -> process shard k % shard_count; within
+    // the shard its tiles are dealt round-robin to the local devices.
+    c.dev.resize(size_t(nd));
+    const int n_tiles = (c.height + c.rows_per_tile - 1) / c.rows_per_tile;
+    int local_tile = 0;
+    for (int k = 0; k < n_tiles; ++k) {
+        if (k % c.shard_count != c.shard_index) continue;
+        DeviceState& d = c.dev[size_t(local_tile % nd)];
+        for (int r = k * c.rows_per_tile; r < (k + 1) * c.rows_per_tile && r < c.height; ++r) { d.rows.push_back(r); c.rows.push_back(r); }
+        ++local_tile;
+    }
+
+    if (c.precision == PTC_FP64) flatten<double>(job, c.scene64);
+    else flatten<float>(job, c.scene32);
+
+    int64_t h2d = 0;
+    const size_t frame_px = size_t(c.width) * c.height;
+    for (int i = 0; i < nd; ++i) {
+        DeviceState& d = c.dev[size_t(i)];
+        d.device = devices[size_t(i)];
+        CUDA_OK(cudaSetDevice(d.device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, d.device));
+        if (prop.major < 10) fail("device %d (%s) is sm_%d%d; libptcuda is built for sm_100a only", d.device, prop.name, prop.major, prop.minor);
+        d.sm_count = prop.multiProcessorCount;
+        CUDA_OK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreate(&d.ev0));
+        CUDA_OK(cudaEventCreate(&d.ev1));
+        if (c.precision == PTC_FP64) upload_scene<double>(c, d, c.scene64, h2d);
+        else upload_scene<float>(c, d, c.scene32, h2d);
+        for (int k = 0; k < 3; ++k) {
+            if (!job.tex[k]) continue;
+            size_t bytes = size_t(c.tex_w[k]) * c.tex_h[k] * c.tex_layers[k] * 4;
+            d.tex[k] = dmalloc(d, bytes);
+            CUDA_OK(cudaMemcpyAsync(d.tex[k], job.tex[k], bytes, cudaMemcpyHostToDevice, d.stream));
+            h2d += int64_t(bytes);
+        }
+        d.seeds = static_cast<double*>(dmalloc(d, frame_px * sizeof(double)));
+        CUDA_OK(cudaMemcpyAsync(d.seeds, job.seeds, frame_px * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+        h2d += int64_t(frame_px * sizeof(double));
+        d.row_map = static_cast<int*>(upload(d, d.rows, h2d));
+        const size_t px = d.rows.size() * size_t(c.width);
+        d.out = static_cast<double*>(dmalloc(d, px * 4 * sizeof(double)));
+        // Small frames cannot fill 148 SMs with one thread per pixel: split each pixel's samples
+        // into interleaved slices until there are ~4 resident-warp sets of work.
+        const long long want = (long long)d.sm_count * 2048 * 2;
+        long long sl = px ? (want + (long long)px - 1) / (long long)px : 1;
+        if (sl > c.samples) sl = c.samples;
+        if (sl > 64) sl = 64;
+        if (sl < 1) sl = 1;
+        d.slices = int(sl);
+        if (d.slices > 1) d.partial = static_cast<double*>(dmalloc(d, size_t(d.slices) * px * 4 * sizeof(double)));
+    }
+    if (nd > 1) {
+        DeviceState& d0 = c.dev[0];
+        CUDA_OK(cudaSetDevice(d0.device));
+        c.gather = static_cast<double*>(dmalloc(d0, c.rows.size() * size_t(c.width) * 4 * sizeof(double)));
+        c.peer_ok = true;
+        for (int i = 1; i < nd; ++i) {
+            int can = 0;
+            CUDA_OK(cudaDeviceCanAccessPeer(&can, d0.device, c.dev[size_t(i)].device));
+            if (!can) { c.peer_ok = false; continue; }
+            cudaError_t pe = cudaDeviceEnablePeerAccess(c.dev[size_t(i)].device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) c.peer_ok = false;
+            cudaGetLastError();
+        }
+    }
+    for (DeviceState& d : c.dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
+    c.stats.upload_ms = ms_since(t0);
+    c.stats.h2d_bytes = h2d;
+    c.stats.n_devices = nd;
+    c.stats.rows = int(c.rows.size());
+    c.stats.paths = int64_t(c.rows.size()) * c.width * c.samples;
+    return guard.release();
+}
+
+void trace_impl(ptc_context& c) {
+    c.stats.kernel_launches = 0;
+    for (DeviceState& d : c.dev) {
+        CUDA_OK(cudaSetDevice(d.device));
+        CUDA_OK(cudaEventRecord(d.ev0, d.stream));
+        if (c.precision == PTC_FP64) launch<double>(c, d, c.scene64);
+        else launch<float>(c, d, c.scene32);
+        CUDA_OK(cudaEventRecord(d.ev1, d.stream));
+    }
+    double worst = 0.0;
+    for (DeviceState& d : c.dev) {
+        CUDA_OK(cudaSetDevice(d.device));
+        CUDA_OK(cudaStreamSynchronize(d.stream));
+        CUDA_OK(cudaEventElapsedTime(&d.last_ms, d.ev0, d.ev1));
+        if (d.last_ms > worst) worst = d.last_ms;
+    }
+    c.stats.kernel_ms = worst;
+}
+
+// Position of frame row `r` inside the packed row list of the context.
+void read_impl(ptc_context& c, double* out) {
+    auto t0 = Clock::now();
+    const size_t row_bytes = size_t(c.width) * 4 * sizeof(double);
+    c.stats.d2h_bytes = 0; c.stats.p2p_bytes = 0;
+    const int nd = int(c.dev.size());
+    if (nd == 1) {
+        DeviceState& d = c.dev[0];
+        CUDA_OK(cudaSetDevice(d.device));
+        CUDA_OK(cudaMemcpyAsync(out, d.out, d.rows.size() * row_bytes, cudaMemcpyDeviceToHost, d.stream));
+        CUDA_OK(cudaStreamSynchronize(d.stream));
+        c.stats.d2h_bytes = int64_t(d.rows.size() * row_bytes);
+    } else {
+        // Device i owns local tiles i, i+nd, i+2nd, ...: one strided 2-D copy per device places them
+        // in the packed frame (tile pitch nd*tile_bytes).  With peer access the copies run
+        // device->device over NVLink into dev[0] and a single D2H follows; otherwise each device
+        // copies straight into the host buffer.
+        const size_t tile_bytes = row_bytes * size_t(c.rows_per_tile);
+        for (int i = 0; i < nd; ++i) {
+            DeviceState& d = c.dev[size_t(i)];
+            if (d.rows.empty()) continue;
+            CUDA_OK(cudaSetDevice(d.device));
+            const size_t full_tiles = d.rows.size() / size_t(c.rows_per_tile);
+            const size_t tail_rows = d.rows.size() % size_t(c.rows_per_tile);
+            char* dst_base = c.peer_ok ? reinterpret_cast<char*>(c.gather) : reinterpret_cast<char*>(out);
+            const cudaMemcpyKind kind = c.peer_ok ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            if (full_tiles)
+                CUDA_OK(cudaMemcpy2DAsync(dst_base + size_t(i) * tile_bytes, size_t(nd) * tile_bytes, d.out, tile_bytes, tile_bytes, full_tiles, kind, d.stream));
+            if (tail_rows)
+                CUDA_OK(cudaMemcpyAsync(dst_base + (full_tiles * size_t(nd) + size_t(i)) * tile_bytes, reinterpret_cast<char*>(d.out) + full_tiles * tile_bytes,
+                                        tail_rows * row_bytes, kind, d.stream));
+            if (c.peer_ok) c.stats.p2p_bytes += int64_t(d.rows.size() * row_bytes); else c.stats.d2h_bytes += int64_t(d.rows.size() * row_bytes);
+        }
+        for (DeviceState& d : c.dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
+        if (c.peer_ok) {
+            DeviceState& d0 = c.dev[0];
+            CUDA_OK(cudaSetDevice(d0.device));
+            CUDA_OK(cudaMemcpyAsync(out, c.gather, c.rows.size() * row_bytes, cudaMemcpyDeviceToHost, d0.stream));
+            CUDA_OK(cudaStreamSynchronize(d0.stream));
+            c.stats.d2h_bytes = int64_t(c.rows.size() * row_bytes);
+        }
+    }
+    c.stats.read_ms = ms_since(t0);
+}
+
+template <typename F> int guarded(char* err, int errlen, F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(err, errlen, e.what());
+        cudaGetLastError();
+        return 1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ptc_version(void) { return "libptcuda 0.1 (sm_100a)"; }
+
+int ptc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ptc_device_name(int index, char* buf, int buflen) {
+    if (!buf || buflen <= 0) return 1;
+    buf[0] = 0;
+    int n = ptc_device_count();
+    if (index < 0 || index >= n) return 1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, index) != cudaSuccess) { cudaGetLastError(); return 1; }
+    std::snprintf(buf, size_t(buflen), "%s", prop.name);
+    return 0;
+}
+
+int ptc_open(const ptc_job* job, ptc_context** ctx, char* err, int errlen) {
+    if (ctx) *ctx = nullptr;
+    return guarded(err, errlen, [&] {
+        if (!job || !ctx) fail("ptc_open: NULL argument");
+        *ctx = open_impl(*job);
+    });
+}
+
+int ptc_trace(ptc_context* ctx, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx) fail("ptc_trace: NULL context");
+        trace_impl(*ctx);
+    });
+}
+
+int ptc_read(ptc_context* ctx, double* out_rgba, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx || !out_rgba) fail("ptc_read: NULL argument");
+        read_impl(*ctx, out_rgba);
+    });
+}
+
+int ptc_get_stats(const ptc_context* ctx, ptc_stats* stats) {
+    if (!ctx || !stats) return 1;
+    *stats = ctx->stats;
+    return 0;
+}
+
+void ptc_close(ptc_context* ctx) { destroy(ctx); }
+
+int ptc_set_seeds(ptc_context* ctx, const double* seeds, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx || !seeds) fail("ptc_set_seeds: NULL argument");
+        const size_t bytes = size_t(ctx->width) * ctx->height * sizeof(double);
+        for (DeviceState& d : ctx->dev) {
+            CUDA_OK(cudaSetDevice(d.device));
+            CUDA_OK(cudaMemcpyAsync(d.seeds, seeds, bytes, cudaMemcpyHostToDevice, d.stream));
+        }
+        for (DeviceState& d : ctx->dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
+    });
+}
+
+int ptc_device_framebuffer(ptc_context* ctx, int local_index, void** dev_ptr, int64_t* n_doubles, int32_t* cuda_device) {
+    if (!ctx || local_index < 0 || local_index >= int(ctx->dev.size())) return 1;
+    DeviceState& d = ctx->dev[size_t(local_index)];
+    if (dev_ptr) *dev_ptr = d.out;
+    if (n_doubles) *n_doubles = int64_t(d.rows.size()) * ctx->width * 4;
+    if (cuda_device) *cuda_device = d.device;
+    return 0;
+}
+
+int ptc_shard_rows(const ptc_context* ctx, int32_t* rows, int cap) {
+    if (!ctx) return 0;
+    const int n = int(ctx->rows.size());
+    if (rows) for (int i = 0; i < n && i < cap; ++i) rows[i] = ctx->rows[size_t(i)];
+    return n;
+}
+
+int ptc_render(const ptc_job* job, double* out_rgba, char* err, int errlen) {
+    ptc_context* ctx = nullptr;
+    int rc = ptc_open(job, &ctx, err, errlen);
+    if (rc != 0) return rc;
+    rc = ptc_trace(ctx, err, errlen);
+    if (rc == 0) rc = ptc_read(ctx, out_rgba, err, errlen);
+    ptc_close(ctx);
+    return rc;
+}
+
+// Test hook (not part of the drop-in surface): evaluate noise3D on the device.
+int ptc_debug_noise3d(const float* xyz, int n, int rng_mode, float* out, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!xyz || !out || n < 0) fail("ptc_debug_noise3d: bad argument");
+        if (ptc_device_count() <= 0) fail("no usable CUDA device; libptcuda has no CPU fallback");
+        float *dx = nullptr, *dout = nullptr;
+        CUDA_OK(cudaSetDevice(0));
+        CUDA_OK(cudaMalloc(&dx, size_t(n) * 3 * sizeof(float) + 16));
+        CUDA_OK(cudaMalloc(&dout, size_t(n) * sizeof(float) + 16));
+        CUDA_OK(cudaMemcpy(dx, xyz, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice));
+        if (n > 0) ptk::noise3d_kernel<<<(n + 255) / 256, 256>>>(dx, dout, n, rng_mode);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(out, dout, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaFree(dx); cudaFree(dout);
+        CUDA_OK(e);
+    });
+}
+
+}  // extern "C"
