@@ -131,6 +131,12 @@ int ptc_device_framebuffer(ptc_context *ctx, int local_index, void **dev_ptr, in
 /* Rows owned by this context, in increasing order; returns the count, fills at most `cap`. */
 int ptc_shard_rows(const ptc_context *ctx, int32_t *rows, int cap);
 
+/* The same ownership rule as a pure host function (no device needed): rows of a `height`-row
+ * frame that belong to shard `shard_index` of `shard_count` with `rows_per_tile`-row tiles
+ * (0 => 4).  Returns the count, fills at most `cap`; -1 on bad arguments. */
+int ptc_plan_rows(int32_t height, int32_t rows_per_tile, int32_t shard_index, int32_t shard_count,
+                  int32_t *rows, int cap);
+
 const char *ptc_version(void);
 
 #ifdef __cplusplus

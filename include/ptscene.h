@@ -58,8 +58,9 @@ void    pts_split_bounds(const double *bbmin4, const double *bbmax4, double *out
  * scene holding a single group object (for objparser_test.go / bvh_test.go style checks). */
 pts_scene *pts_scene_from_obj(const char *obj_text, const char *mtl_dir, int32_t vertex_normals,
                               int32_t divide_threshold, char *err, int errlen);
-/* statistics of the parsed model behind a pts_scene_from_obj scene: vertices, normals, groups, triangles */
-void    pts_obj_stats(const pts_scene *s, int32_t *out4);
+/* statistics of the parsed model behind a pts_scene_from_obj scene: vertices, normals, groups, triangles,
+ * ignored lines */
+void    pts_obj_stats(const pts_scene *s, int32_t *out5);
 
 #ifdef __cplusplus
 }

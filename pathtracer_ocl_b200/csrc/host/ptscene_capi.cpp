@@ -15,7 +15,7 @@ struct pts_scene {
     SceneBuffers buf;
     std::vector<uint8_t> tex[3];
     int32_t tex_w[3] = {0, 0, 0}, tex_h[3] = {0, 0, 0}, tex_layers[3] = {0, 0, 0};
-    int32_t obj_stats[4] = {0, 0, 0, 0};
+    int32_t obj_stats[5] = {0, 0, 0, 0, 0};
 };
 
 static void set_err(char* err, int errlen, const std::string& msg) {
@@ -224,13 +224,13 @@ pts_scene* pts_scene_from_obj(const char* obj_text, const char* mtl_dir, int32_t
         auto* out = new pts_scene;
         out->buf = build_scene_buffers(sc);
         out->obj_stats[0] = int32_t(model.vertices.size()); out->obj_stats[1] = int32_t(model.normals.size());
-        out->obj_stats[2] = int32_t(model.groups.size()); out->obj_stats[3] = tris;
+        out->obj_stats[2] = int32_t(model.groups.size()); out->obj_stats[3] = tris; out->obj_stats[4] = model.ignored_lines;
         return out;
     } catch (const std::exception& e) {
         set_err(err, errlen, e.what());
         return nullptr;
     }
 }
-void pts_obj_stats(const pts_scene* s, int32_t* out4) { for (int i = 0; i < 4; ++i) out4[i] = s->obj_stats[i]; }
+void pts_obj_stats(const pts_scene* s, int32_t* out5) { for (int i = 0; i < 5; ++i) out5[i] = s->obj_stats[i]; }
 
 }  // extern "C"

@@ -532,6 +532,21 @@ int ptc_shard_rows(const ptc_context* ctx, int32_t* rows, int cap) {
     return n;
 }
 
+int ptc_plan_rows(int32_t height, int32_t rows_per_tile, int32_t shard_index, int32_t shard_count, int32_t* rows, int cap) {
+    if (height < 0) return -1;
+    const int rpt = rows_per_tile > 0 ? rows_per_tile : 4;
+    const int sc = shard_count > 1 ? shard_count : 1;
+    const int si = shard_count > 1 ? shard_index : 0;
+    if (si < 0 || si >= sc) return -1;
+    int n = 0;
+    for (int r = 0; r < height; ++r) {
+        if ((r / rpt) % sc != si) continue;
+        if (rows && n < cap) rows[n] = r;
+        ++n;
+    }
+    return n;
+}
+
 int ptc_render(const ptc_job* job, double* out_rgba, char* err, int errlen) {
     ptc_context* ctx = nullptr;
     int rc = ptc_open(job, &ctx, err, errlen);

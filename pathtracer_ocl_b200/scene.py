@@ -169,14 +169,14 @@ def build_scene(name: str = "default", width: int = 640, height: int = 480, aper
 
 
 def scene_from_obj(text: str, mtl_dir: str = "", vertex_normals: bool = False, divide_threshold: int = 0):
-    """Parse OBJ text -> single-group scene buffers + (vertices, normals, groups, triangles) counts."""
+    """Parse OBJ text -> single-group scene buffers + (vertices, normals, groups, triangles, ignored lines) counts."""
     L = lib()
     err = C.create_string_buffer(512)
     h = L.pts_scene_from_obj(text.encode(), mtl_dir.encode(), int(vertex_normals), divide_threshold, err, 512)
     if not h:
         raise RuntimeError(err.value.decode())
     try:
-        stats = (C.c_int32 * 4)()
+        stats = (C.c_int32 * 5)()
         L.pts_obj_stats(h, stats)
         return _harvest(h, "obj", 4, 4), tuple(stats)
     finally:

@@ -51,7 +51,7 @@ class PtcStats(C.Structure):
 
 
 EXPORTS = ["ptc_device_count", "ptc_device_name", "ptc_render", "ptc_open", "ptc_trace", "ptc_read", "ptc_get_stats",
-           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_version"]
+           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_plan_rows", "ptc_version"]
 
 _lib = None
 
@@ -77,8 +77,20 @@ def lib() -> C.CDLL:
                                              C.POINTER(C.c_int32)]
         L.ptc_shard_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int]
         L.ptc_debug_noise3d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_plan_rows.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int]
         _lib = L
     return _lib
+
+
+def plan_rows(height: int, shard_index: int = 0, shard_count: int = 1, rows_per_tile: int = 0) -> np.ndarray:
+    """Frame rows owned by one shard (interleaved scanline tiles); host-only, no device needed."""
+    L = lib()
+    n = L.ptc_plan_rows(height, rows_per_tile, shard_index, shard_count, None, 0)
+    if n < 0:
+        raise ValueError("bad shard arguments")
+    buf = (C.c_int32 * max(n, 1))()
+    L.ptc_plan_rows(height, rows_per_tile, shard_index, shard_count, buf, n)
+    return np.array(buf[:n], dtype=np.int32)
 
 
 class PtcError(RuntimeError):

@@ -1,0 +1,237 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libptcuda), against the CPU oracle
+on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full
+frame size -- through size-independent properties.  Run on the B200 box: pytest -m gpu.
+
+Tolerances are BASELINE.json's: at 1 spp with the reference's RNG stream reproduced, >= 99.9% of
+pixels within 1e-3 absolute per channel in fp32 mode and 1e-6 in fp64 mode; converged (1024 spp)
+images within 0.5% relative RMSE."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from pathtracer_ocl_b200 import scene as S, trace as T
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {T.FP32: 1e-3, T.FP64: 1e-6}
+PRECISIONS = [pytest.param(T.FP32, id="fp32"), pytest.param(T.FP64, id="fp64")]
+
+
+def frac_within(img, ref, tol):
+    err = np.abs(img[..., :3] - ref[..., :3]).max(axis=-1)
+    return float((err <= tol).mean()), float(np.nanmax(err))
+
+
+def rel_rmse(img, ref):
+    d = img[..., :3] - ref[..., :3]
+    return float(np.sqrt(np.mean(d * d)) / np.sqrt(np.mean(ref[..., :3] ** 2)))
+
+
+def test_device_is_a_b200_class_gpu():
+    devs = T.list_devices()
+    assert devs and devs[0].startswith("Index: 0 Type: GPU Name: ")
+
+
+def test_rng_stream_is_bit_identical_to_the_oracle():
+    rng = np.random.default_rng(1)
+    xyz = np.concatenate([(rng.random((300000, 3)) * [1, 4096, 4096]), (rng.random((100000, 3)) * [1, 4096 ** 2, 10]),
+                          (rng.random((100000, 3)) * [10, 4096, 1]), np.zeros((1, 3))]).astype(np.float32)
+    ref = np.empty(len(xyz), np.float32)
+    O.lib().oracle_noise3d_array(xyz.ctypes.data, len(xyz), ref.ctypes.data)
+    dev = T.debug_noise3d(xyz, T.RNG_PARITY)
+    assert np.array_equal(ref.view(np.uint32), dev.view(np.uint32))
+    fast = T.debug_noise3d(xyz, T.RNG_FAST)          # different stream, same distribution
+    assert fast.min() >= 0.0 and fast.max() < 1.0 and abs(fast.mean() - 0.5) < 0.01
+
+
+# scene, W, H, spp, aperture, focal length -- every material / shape / texture branch of the kernel
+CASES = [
+    ("default", 160, 120, 1, 0.0, 0.0),            # BASELINE config 1 (reduced frame): planes, spheres, cylinder, cube, mirror
+    ("reference", 160, 120, 1, 0.15, 1.6),         # config 2 scene: DoF, samples == 1
+    ("reference", 96, 72, 5, 0.15, 1.6),           # DoF with the NaN sample-0 quirk (samples >= 3)
+    ("transparency", 128, 96, 2, 0.0, 0.0),        # refraction in/out, glass + mirror
+    ("transparency_quad_lights", 96, 72, 2, 0.0, 0.0),
+    ("transparency_f_light", 96, 72, 1, 0.0, 0.0),
+    ("reflection", 96, 72, 2, 0.0, 0.0),
+    ("teapot", 96, 72, 1, 0.0, 0.0),               # config 3 scene: BVH, computed vertex normals, reflectivity 0.2
+    ("gopher", 96, 72, 1, 0.0, 0.0),               # config 4 scene: 13 root children, per-triangle colours
+    ("gopher-window", 64, 48, 1, 0.0, 0.0),        # 15 objects
+    ("christian", 64, 48, 1, 0.0, 0.0),            # 15 objects, open cylinders with reflectivity
+    ("transparent_teapot", 96, 72, 2, 0.0, 0.0),   # thin glass (refractive index -1)
+    ("textures", 96, 72, 2, 0.0, 0.0),             # config 5: plane textures + normal maps + sphere maps
+    ("envmap", 96, 72, 2, 0.0, 0.0),               # config 5: emissive textured sky sphere
+    ("cubemap", 96, 72, 2, 0.0, 0.0),              # config 5: cube-cross sky + mesh
+]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name,W,H,spp,ap,fl", CASES, ids=[f"{c[0]}-{c[1]}x{c[2]}@{c[3]}" for c in CASES])
+def test_low_spp_pixel_parity(name, W, H, spp, ap, fl, precision):
+    sc = S.build_scene(name, W, H, ap, fl, tex_scale=16)
+    seeds = S.make_seeds(0x5EED0000 + W + spp, W * H)
+    ref, _ = O.trace(sc, seeds, spp, precision=1)
+    img = T.render_scene(sc, spp, seeds, precision=precision)
+    assert not np.isnan(img).any() and np.all(img[..., 3] == 1.0)
+    frac, worst = frac_within(img, ref, TOL[precision])
+    assert frac >= 0.999, f"{frac * 100:.3f}% of pixels within {TOL[precision]:g} (worst {worst:.3e})"
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))), ids=os.path.basename)
+def test_against_committed_golden_fixtures(path):
+    g = np.load(path)
+    w, h, spp = int(g["width"]), int(g["height"]), int(g["spp"])
+    sc = S.build_scene(str(g["scene"]), w, h, float(g["aperture"]), float(g["focal_length"]), tex_scale=int(g["tex_scale"]))
+    seeds = S.make_seeds(int(g["seed"]), w * h)
+    for precision in (T.FP64, T.FP32):
+        img = T.render_scene(sc, spp, seeds, precision=precision)
+        frac, worst = frac_within(img, g["rgba"], TOL[precision])
+        assert frac >= 0.999, f"precision {precision}: {frac * 100:.3f}% within tolerance (worst {worst:.3e})"
+
+
+@pytest.mark.parametrize("name,W,H,ap,fl", [("reference", 96, 72, 0.15, 1.6), ("teapot", 64, 48, 0.0, 0.0),
+                                            ("transparency", 64, 48, 0.0, 0.0), ("textures", 64, 48, 0.0, 0.0)])
+def test_converged_1024spp_rmse(name, W, H, ap, fl):
+    spp = 1024
+    sc = S.build_scene(name, W, H, ap, fl, tex_scale=16)
+    seeds = S.make_seeds(0xC0FFEE, W * H)
+    ref, _ = O.trace(sc, seeds, spp, precision=1)
+    for precision in (T.FP32, T.FP64):
+        img = T.render_scene(sc, spp, seeds, precision=precision)     # small frame -> exercises sample slices
+        assert rel_rmse(img, ref) <= 0.005, f"precision {precision}: relative RMSE {rel_rmse(img, ref):.5f}"
+    # the fast RNG draws a different (equally distributed) stream: compare statistically
+    fast = T.render_scene(sc, spp, seeds, precision=T.FP32, rng_mode=T.RNG_FAST)
+    assert abs(fast[..., :3].mean() - ref[..., :3].mean()) <= 0.01 * ref[..., :3].mean()
+    blocks = lambda a: a[: H // 8 * 8, : W // 8 * 8, :3].reshape(H // 8, 8, W // 8, 8, 3).mean(axis=(1, 3))
+    assert rel_rmse(blocks(fast), blocks(ref)) <= 0.03
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(1, 1), (7, 3), (33, 5), (8, 4), (9, 9)])
+def test_ragged_frame_sizes(W, H):
+    sc = S.build_scene("default", W, H)
+    seeds = S.make_seeds(W * 100 + H, W * H)
+    ref, _ = O.trace(sc, seeds, 2, 1)
+    img = T.render_scene(sc, 2, seeds, precision=T.FP64)
+    assert img.shape == (H, W, 4)
+    assert np.abs(img - ref).max() <= 1e-6
+
+
+def test_sixteen_objects_is_the_limit():
+    sc = S.build_scene("gopher-window", 48, 36)
+    assert sc.n_objects == 15
+    o = sc.objects.copy().reshape(15, 1024)
+    o16 = np.concatenate([o, o[-1:]])                 # duplicate the light: 16 objects
+    seeds = S.make_seeds(3, 48 * 36)
+    sc16 = S.SceneBuffers("x", 48, 36, o16.reshape(-1), sc.triangles, sc.groups, sc.camera)
+    ref, _ = O.trace(sc16, seeds, 1, 1)
+    img = T.Trace(sc16.objects, sc16.triangles, sc16.groups, 0, 1, sc16.camera, seeds=seeds, precision=T.FP64).reshape(36, 48, 4)
+    assert np.abs(img - ref).max() <= 1e-6
+    with pytest.raises(T.PtcError, match="at most 16"):
+        T.Trace(np.concatenate([o16, o[-1:]]).reshape(-1), sc.triangles, sc.groups, 0, 1, sc.camera, seeds=seeds)
+
+
+def test_scene_without_triangles_accepts_null_buffers():
+    sc = S.build_scene("reference", 32, 24)
+    seeds = S.make_seeds(4, 32 * 24)
+    a = T.Trace(sc.objects, None, None, 0, 1, sc.camera, seeds=seeds, precision=T.FP64)
+    # the reference pads empty slices with one zeroed record (ocltracer.go:106-120): same result
+    b = T.Trace(sc.objects, np.zeros(512, np.uint8), np.zeros(256, np.uint8), 0, 1, sc.camera, seeds=seeds, precision=T.FP64)
+    assert np.array_equal(a, b)
+
+
+def test_device_index_rules():
+    sc = S.build_scene("default", 16, 12)
+    seeds = S.make_seeds(5, 16 * 12)
+    a = T.Trace(sc.objects, None, None, -3, 1, sc.camera, seeds=seeds)      # negative -> 0 (ocltracer.go:138-140)
+    b = T.Trace(sc.objects, None, None, 0, 1, sc.camera, seeds=seeds)
+    assert np.array_equal(a, b)
+    with pytest.raises(T.PtcError, match="out of bounds"):                   # ocltracer.go:135-137
+        T.Trace(sc.objects, None, None, 99, 1, sc.camera, seeds=seeds)
+
+
+def test_unseeded_trace_draws_fresh_seeds_like_the_reference():
+    sc = S.build_scene("default", 32, 24)
+    a = T.Trace(sc.objects, None, None, 0, 1, sc.camera)
+    b = T.Trace(sc.objects, None, None, 0, 1, sc.camera)
+    assert a.shape == (32 * 24 * 4,) and not np.array_equal(a, b)
+
+
+def test_phase_api_set_seeds_and_stats():
+    sc = S.build_scene("transparency", 64, 48)
+    s1, s2 = S.make_seeds(6, 64 * 48), S.make_seeds(7, 64 * 48)
+    with T.open_scene(sc, 2, s1, precision=T.FP64) as ctx:
+        ctx.trace()
+        a = ctx.read().copy()
+        ctx.set_seeds(s2)
+        ctx.trace()
+        b = ctx.read().copy()
+        st = ctx.stats()
+    assert np.array_equal(a.reshape(48, 64, 4), T.render_scene(sc, 2, s1, precision=T.FP64))
+    assert np.array_equal(b.reshape(48, 64, 4), T.render_scene(sc, 2, s2, precision=T.FP64))
+    assert st["paths"] == 64 * 48 * 2 and st["kernel_launches"] >= 1 and st["kernel_ms"] > 0
+    assert st["d2h_bytes"] == 64 * 48 * 32 and st["h2d_bytes"] > 64 * 48 * 8
+
+
+def test_sample_slices_match_single_slice_sum():
+    # 16x12 pixels at 256 spp is split into sample slices on the device; the result must equal the oracle's
+    sc = S.build_scene("default", 16, 12)
+    seeds = S.make_seeds(8, 16 * 12)
+    ref, _ = O.trace(sc, seeds, 256, 1)
+    img = T.render_scene(sc, 256, seeds, precision=T.FP64)
+    assert np.abs(img - ref).max() <= 1e-9
+
+
+@pytest.mark.parametrize("world,rpt", [(2, 4), (3, 4), (8, 4), (2, 1)])
+def test_process_shards_tile_the_frame(world, rpt):
+    W, H = 64, 50
+    sc = S.build_scene("default", W, H)
+    seeds = S.make_seeds(9, W * H)
+    full = T.render_scene(sc, 1, seeds, precision=T.FP32)
+    seen = np.zeros(H, bool)
+    for r in range(world):
+        with T.open_scene(sc, 1, seeds, precision=T.FP32, shard_index=r, shard_count=world, rows_per_tile=rpt) as ctx:
+            assert np.array_equal(ctx.rows, T.plan_rows(H, r, world, rpt))
+            ctx.trace()
+            part = ctx.read().reshape(len(ctx.rows), W, 4)
+            assert np.array_equal(part, full[ctx.rows])
+            seen[ctx.rows] = True
+    assert seen.all()
+
+
+# ---- BASELINE.json frame size: size-independent properties ------------------------------------------------
+def test_full_size_reference_frame_properties():
+    """Config 2's frame (1280x960, aperture 0.15, focal length 1.6) at 2 spp: deterministic, alpha 1,
+    shard-invariant, and a strip of rows equals the oracle's."""
+    W, H, spp = 1280, 960, 2
+    sc = S.build_scene("reference", W, H, 0.15, 1.6)
+    seeds = S.make_seeds(0x5EED0002, W * H)
+    a = T.render_scene(sc, spp, seeds, precision=T.FP32)
+    b = T.render_scene(sc, spp, seeds, precision=T.FP32)
+    assert np.array_equal(a, b)                                  # same seeds -> bit-identical frames
+    assert np.all(a[..., 3] == 1.0) and not np.isnan(a).any() and a[..., :3].min() >= 0.0
+    with T.open_scene(sc, spp, seeds, precision=T.FP32, shard_index=3, shard_count=8) as ctx:
+        ctx.trace()
+        part = ctx.read().reshape(len(ctx.rows), W, 4)
+    assert np.array_equal(part, a[T.plan_rows(H, 3, 8)])
+    ref, _ = O.trace(sc, seeds, spp, 1, rows=(470, 490))
+    frac, worst = frac_within(a[470:490], ref, 1e-3)
+    assert frac >= 0.999, (frac, worst)
+    # coarse sanity of the picture: the ceiling light is bright (sample 0 of 2 is the black NaN-ray
+    # sample, so a direct view of the emitter averages ~0.5), the left wall is red, the right one blue
+    assert a[190:220, 600:680, :3].mean() > 0.35
+    assert a[400:600, :100, 0].mean() > a[400:600, :100, 2].mean()
+    assert a[400:600, -100:, 2].mean() > a[400:600, -100:, 0].mean()
+
+
+def test_full_size_teapot_strip_matches_oracle():
+    W, H = 1280, 960
+    sc = S.build_scene("teapot", W, H)
+    seeds = S.make_seeds(0x5EED0003, W * H)
+    img = T.render_scene(sc, 1, seeds, precision=T.FP64)
+    ref, _ = O.trace(sc, seeds, 1, 1, rows=(640, 660))            # rows through the teapot body
+    frac, worst = frac_within(img[640:660], ref, 1e-6)
+    assert frac >= 0.999, (frac, worst)
