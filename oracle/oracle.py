@@ -32,11 +32,12 @@ def lib() -> C.CDLL:
             build()
         L = C.CDLL(_LIB_PATH)
         L.oracle_counter_name.restype = C.c_char_p
-        L.oracle_trace.restype = C.c_int
-        L.oracle_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                   C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                   C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                   C.c_void_p, C.c_void_p]
+        L.oracle_trace2.restype = C.c_int
+        L.oracle_trace2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p]
+        L.oracle_noise3d_array_mode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_noise3d.restype = C.c_float
         L.oracle_noise3d.argtypes = [C.c_float] * 3
         L.oracle_sinf.restype = C.c_float
@@ -61,7 +62,7 @@ def counter_names():
 
 
 def trace(scene, seeds: np.ndarray, samples: int, precision: int = 1, rows: Optional[Tuple[int, int]] = None,
-          nthreads: Optional[int] = None) -> Tuple[np.ndarray, Dict[str, int]]:
+          nthreads: Optional[int] = None, rng_mode: int = 0) -> Tuple[np.ndarray, Dict[str, int]]:
     """Render rows [rows[0], rows[1]) of `scene` (a pathtracer_ocl_b200.scene.SceneBuffers).
 
     Returns (rgba float64 [nrows, W, 4], event counters)."""
@@ -84,11 +85,11 @@ def trace(scene, seeds: np.ndarray, samples: int, precision: int = 1, rows: Opti
             ptrs[c] = t.ctypes.data
             tl[c], th[c], tw[c] = t.shape[0], t.shape[1], t.shape[2]
     counters = np.zeros(L.oracle_counter_count(), dtype=np.uint64)
-    rc = L.oracle_trace(scene.objects.ctypes.data, scene.n_objects,
+    rc = L.oracle_trace2(scene.objects.ctypes.data, scene.n_objects,
                         scene.triangles.ctypes.data if scene.n_triangles else None, scene.n_triangles,
                         scene.groups.ctypes.data if scene.n_groups else None, scene.n_groups,
-                        scene.camera.ctypes.data, ptrs, tw, th, tl, seeds.ctypes.data, samples, precision, r0, r1,
-                        nthreads, out.ctypes.data, counters.ctypes.data)
+                        scene.camera.ctypes.data, ptrs, tw, th, tl, seeds.ctypes.data, samples, precision, rng_mode, r0, r1,
+                         nthreads, out.ctypes.data, counters.ctypes.data)
     if rc != 0:
         raise RuntimeError(f"oracle_trace failed with code {rc}")
     return out, dict(zip(counter_names(), (int(v) for v in counters)))

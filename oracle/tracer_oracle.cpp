@@ -86,6 +86,7 @@ template <typename Real> struct Scene {
     Cam<Real> cam;
     Texture tex[3];
     unsigned samples;
+    int rng_fast;   // 0: correctly rounded sine (parity stream); 1: the reproducible fast stream (canon_rng.h)
     Real PI, EPSILON;
 };
 
@@ -236,7 +237,7 @@ struct Tracer {
     Ctx ctx;
     explicit Tracer(const Scene<Real>& s) : sc(s) { std::memset(cnt, 0, sizeof cnt); }
 
-    float noise(float x, float y, float z) { cnt[C_NOISE]++; return canon_noise3d(x, y, z); }
+    float noise(float x, float y, float z) { cnt[C_NOISE]++; return canon_noise3d_mode(x, y, z, sc.rng_fast); }
 
     // tracer.cl:537-742.  Returns object index (-1 = none), t and the winning record's slot.
     int closest(V4<Real> ro, V4<Real> rd, Real& out_t, int& slot) {
@@ -560,7 +561,8 @@ struct Tracer {
 template <typename Real>
 void build_scene(Scene<Real>& sc, const ptw_object* objs, int n_obj, const ptw_triangle* tris, int n_tri, const ptw_group* groups,
                  int n_grp, const ptw_camera* cam, const uint8_t* const* tex, const int32_t* tw, const int32_t* th,
-                 const int32_t* tl, int samples) {
+                 const int32_t* tl, int samples, int rng_fast) {
+    sc.rng_fast = rng_fast;
     sc.PI = Real(double(3.14159265359f));    // tracer.cl:1
     sc.EPSILON = Real(0.0001);               // tracer.cl:4
     sc.samples = unsigned(samples);
@@ -605,9 +607,9 @@ void build_scene(Scene<Real>& sc, const ptw_object* objs, int n_obj, const ptw_t
 template <typename Real>
 int run(const ptw_object* objs, int n_obj, const ptw_triangle* tris, int n_tri, const ptw_group* groups, int n_grp,
         const ptw_camera* cam, const uint8_t* const* tex, const int32_t* tw, const int32_t* th, const int32_t* tl,
-        const double* seeds, int samples, int row0, int row1, int nthreads, double* out, uint64_t* counters) {
+        const double* seeds, int samples, int rng_fast, int row0, int row1, int nthreads, double* out, uint64_t* counters) {
     Scene<Real> sc;
-    build_scene(sc, objs, n_obj, tris, n_tri, groups, n_grp, cam, tex, tw, th, tl, samples);
+    build_scene(sc, objs, n_obj, tris, n_tri, groups, n_grp, cam, tex, tw, th, tl, samples, rng_fast);
     const int W = cam->width;
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(row0);
@@ -651,25 +653,36 @@ const char* oracle_counter_name(int i) {
 }
 
 // Renders rows [row0,row1) of the frame.  precision: 0 = float arithmetic, 1 = double (tracer.cl).
+// rng_mode: 0 = parity stream, 1 = fast stream (both defined in canon_rng.h).
 // seeds: width*height doubles (whole frame).  out: (row1-row0)*width*4 doubles.
-int oracle_trace(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,
-                 const void* camera, const uint8_t* const* tex, const int32_t* tex_w, const int32_t* tex_h,
-                 const int32_t* tex_layers, const double* seeds, int samples, int precision, int row0, int row1, int nthreads,
-                 double* out, uint64_t* counters) {
+int oracle_trace2(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,
+                  const void* camera, const uint8_t* const* tex, const int32_t* tex_w, const int32_t* tex_h,
+                  const int32_t* tex_layers, const double* seeds, int samples, int precision, int rng_mode, int row0, int row1,
+                  int nthreads, double* out, uint64_t* counters) {
     if (!objects || n_objects < 1 || n_objects > PTW_MAX_OBJECTS || !camera || !seeds || !out || samples < 1) return 1;
     const ptw_camera* cam = static_cast<const ptw_camera*>(camera);
     if (row0 < 0 || row1 > cam->height || row0 > row1) return 2;
     auto* o = static_cast<const ptw_object*>(objects);
     auto* t = static_cast<const ptw_triangle*>(triangles);
     auto* g = static_cast<const ptw_group*>(groups);
-    if (precision == 1) return run<double>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, row0, row1, nthreads, out, counters);
-    return run<float>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, row0, row1, nthreads, out, counters);
+    const int fast = rng_mode != 0;
+    if (precision == 1) return run<double>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, fast, row0, row1, nthreads, out, counters);
+    return run<float>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, fast, row0, row1, nthreads, out, counters);
+}
+
+int oracle_trace(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,
+                 const void* camera, const uint8_t* const* tex, const int32_t* tex_w, const int32_t* tex_h,
+                 const int32_t* tex_layers, const double* seeds, int samples, int precision, int row0, int row1, int nthreads,
+                 double* out, uint64_t* counters) {
+    return oracle_trace2(objects, n_objects, triangles, n_triangles, groups, n_groups, camera, tex, tex_w, tex_h, tex_layers, seeds,
+                         samples, precision, 0, row0, row1, nthreads, out, counters);
 }
 
 // Unit hooks (golden-vector tests).
 float oracle_noise3d(float x, float y, float z) { return canon_noise3d(x, y, z); }
 float oracle_sinf(float x) { return canon_sinf(x); }
 void oracle_noise3d_array(const float* xyz, int n, float* out) { for (int i = 0; i < n; ++i) out[i] = canon_noise3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+void oracle_noise3d_array_mode(const float* xyz, int n, int rng_mode, float* out) { for (int i = 0; i < n; ++i) out[i] = canon_noise3d_mode(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], rng_mode != 0); }
 void oracle_sinf_array(const float* x, int n, float* out) { for (int i = 0; i < n; ++i) out[i] = canon_sinf(x[i]); }
 int oracle_ray_box(const double* o, const double* d, const double* lo, const double* hi) {
     return ray_box<double>({o[0], o[1], o[2], o[3]}, {d[0], d[1], d[2], d[3]}, {lo[0], lo[1], lo[2], lo[3]}, {hi[0], hi[1], hi[2], hi[3]}, 0.0001) ? 1 : 0;

@@ -21,8 +21,12 @@ __device__ __forceinline__ float sin_parity(float x) {
     const double PI_HI = 0x1.921fb54442d18p+1;
     const double PI_LO = 0x1.1a62633145c07p-53;
     double xd = (double)x;
-    long long qi = __double2ll_rn(__dmul_rn(xd, INV_PI));
-    double q = (double)qi;
+    // q = rint(x/pi) by the add-and-subtract-1.5*2^52 trick (exact for |x/pi| < 2^51, ties to even like
+    // rint); the parity of q is the low mantissa bit of the biased sum.  Avoids two 64-bit conversions.
+    const double MAGIC = 6755399441055744.0;
+    double biased = __dadd_rn(__dmul_rn(xd, INV_PI), MAGIC);
+    const int qi = __double2loint(biased);
+    double q = __dadd_rn(biased, -MAGIC);
     double r = __fma_rn(-q, PI_HI, xd);
     r = __fma_rn(-q, PI_LO, r);
     double r2 = __dmul_rn(r, r);
@@ -46,8 +50,10 @@ __device__ __forceinline__ float sin_fast(float x) {
     const double PI_HI = 0x1.921fb54442d18p+1;
     const double PI_LO = 0x1.1a62633145c07p-53;
     double xd = (double)x;
-    int qi = __double2int_rn(xd * INV_PI);       // |x| < 6.7e9 on every call site
-    double q = (double)qi;
+    const double MAGIC = 6755399441055744.0;
+    double biased = __dadd_rn(__dmul_rn(xd, INV_PI), MAGIC);
+    const int qi = __double2loint(biased);
+    double q = __dadd_rn(biased, -MAGIC);
     double rd = __fma_rn(-q, PI_LO, __fma_rn(-q, PI_HI, xd));
     float r = __double2float_rn(rd);
     float r2 = r * r;

@@ -15,13 +15,20 @@
 //   * closest hit is a running minimum in registers (the reference zero-fills a 6.9 KB `context`
 //     per bounce and scans it afterwards, tracer.cl:886, 727-741) and shading is fused into the
 //     segment loop (the reference stores bounces and replays them, 1071-1096 -> 1116-1179);
-//   * the <=16 scene objects live in shared memory as compact affine records read with broadcast
-//     loads (the reference copies 16 KB of 1024-byte records per work-item, tracer.cl:846-849);
+//   * the per-object data the intersection loop needs (affine inverse, type, bounds) travels in the
+//     kernel parameter block, i.e. the constant bank: the loop index is warp-uniform, so the
+//     matrix entries are read through the uniform datapath and feed FFMA directly instead of
+//     costing load instructions and registers (the reference copies 16 KB of 1024-byte records
+//     into __local per work-item, tracer.cl:846-849); material data is fetched per hit;
 //   * the BVH is re-emitted in traversal (pre-)order with skip links, so the walk needs no stack
 //     and visits exactly the nodes, in exactly the order, of the reference's stack walk
 //     (tracer.cl:624-714); nodes and triangles are 16-byte-vectorised records (48 B of test data
 //     per triangle instead of a 512-byte stride);
+//   * the depth-of-field lens points depend only on the sample index, so they come from a table
+//     built once on the host instead of two sqrt, a divide and a sincos per path;
 //   * everything is templated on the arithmetic type: float = "fp32 mode", double = tracer.cl.
+//     The fp32 instantiation uses the SFU approximations (rcp / rsqrt / sqrt / sin / cos) for its
+//     own arithmetic; the RNG and the texture filter stay exactly rounded in both modes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,9 +45,13 @@ template <typename R> struct alignas(16) V4 { R x, y, z, w; };
 template <typename R> struct V3 { R x, y, z; };
 
 // ---- scalar math, overloaded on the arithmetic type -------------------------------------------
-__device__ __forceinline__ float m_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ float m_rcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ double m_rcp(double a) { return 1.0 / a; }
+__device__ __forceinline__ float m_div(float a, float b) { return a * m_rcp(b); }
+__device__ __forceinline__ double m_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float m_sqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ double m_sqrt(double a) { return sqrt(a); }
-__device__ __forceinline__ float m_rsqrt(float a) { return rsqrtf(a); }
+__device__ __forceinline__ float m_rsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ double m_rsqrt(double a) { return 1.0 / sqrt(a); }
 __device__ __forceinline__ float m_abs(float a) { return fabsf(a); }
 __device__ __forceinline__ double m_abs(double a) { return fabs(a); }
@@ -48,16 +59,20 @@ __device__ __forceinline__ float m_min(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double m_min(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float m_max(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double m_max(double a, double b) { return fmax(a, b); }
-__device__ __forceinline__ void m_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
-__device__ __forceinline__ void m_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+// sin/cos of an angle in [0, 2*pi): the fp32 version shifts into [-pi, pi) where MUFU.SIN/COS have
+// their best absolute accuracy (~5e-7) and flips the signs back
+__device__ __forceinline__ void m_sincos_2pi(float a, float* s, float* c) {
+    float sa, ca;
+    __sincosf(a - 3.14159265358979f, &sa, &ca);
+    *s = -sa; *c = -ca;
+}
+__device__ __forceinline__ void m_sincos_2pi(double a, double* s, double* c) { sincos(a, s, c); }
 __device__ __forceinline__ float m_acos(float a) { return acosf(a); }
 __device__ __forceinline__ double m_acos(double a) { return acos(a); }
 __device__ __forceinline__ float m_atan2(float a, float b) { return atan2f(a, b); }
 __device__ __forceinline__ double m_atan2(double a, double b) { return atan2(a, b); }
 __device__ __forceinline__ float m_fmod(float a, float b) { return fmodf(a, b); }
 __device__ __forceinline__ double m_fmod(double a, double b) { return fmod(a, b); }
-__device__ __forceinline__ float m_round(float a) { return roundf(a); }
-__device__ __forceinline__ double m_round(double a) { return round(a); }
 template <typename R> __device__ __forceinline__ R m_huge();
 template <> __device__ __forceinline__ float m_huge<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double m_huge<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
@@ -73,24 +88,39 @@ template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) {
 template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { return a * m_rsqrt(dot(a, a)); }
 
 // ---- device scene ------------------------------------------------------------------------------
-// One scene object, converted once on the host from the 1024-byte wire record (ptw_object).  All
+// Scene objects are converted once on the host from the 1024-byte wire records (ptw_object).  All
 // transforms on the path are affine (bottom row 0,0,0,1; points keep w=1, directions w=0), so only
 // the top three rows of the inverse and the 3x3 of the inverse-transpose are kept.
-template <typename R> struct alignas(16) DObj {
-    R inv[12];          // rows 0..2 of `inverse`            (tracer.cl:547-548)
-    R invt[9];          // 3x3 of `inverseTranspose`         (tracer.cl:953)
+//
+// "Hot" half: what the intersection loop reads for EVERY object on EVERY segment; lives in the
+// kernel parameter block (constant bank, uniform loads).
+template <typename R> struct alignas(16) DObjHot {
+    R inv[12];          // rows 0..2 of `inverse` (tracer.cl:547-548)
+    R aux[6];           // cylinder: min_y, max_y; group: bb_min.xyz, bb_max.xyz
+    int type;           // 0 plane 1 sphere 2 cylinder 3 cube 4 group, anything else: never hit
+    int node_begin, node_end;   // group: range of BVH nodes (all root children, in root order)
+    int pad;
+};
+// "Shade" half: read once per hit, indexed by the (lane-varying) hit object; lives in global memory.
+// Ordered so that the common case (an untextured plane) touches only the first 64 bytes (fp32).
+template <typename R> struct alignas(16) DObjShade {
+    int type;
+    int flags;          // bit0 textured, bit1 normal-mapped, bit2 needs the object-space hit point
+    int tex_index, tex_index_nm;
+    R reflectivity, refractive_index, min_y, max_y;
     R color[3];
     R emission[3];
-    R bb_min[3];
-    R bb_max[3];
-    R refractive_index, reflectivity, min_y, max_y;
+    R plane_n[3];       // planes without a normal map: normalize(inverseTranspose * (0,1,0)), precomputed
     R tex_sx, tex_sy, tex_sx_nm, tex_sy_nm;
-    int type;           // 0 plane 1 sphere 2 cylinder 3 cube 4 group
-    int node_begin, node_end;   // group: range of BVH nodes (all root children, in root order)
-    int flags;          // bit0 textured, bit1 normal-mapped
-    int tex_index, tex_index_nm;
-    int pad0, pad1;
+    R pad0;
+    R inv[12];
+    R invt[9];          // 3x3 of `inverseTranspose` (tracer.cl:953)
+    R pad1[3];
 };
+
+// Consecutive objects of one type form a run; the intersection loop dispatches once per run and
+// keeps the reference's object order (ties go to the lower object index, tracer.cl:731-739).
+struct DRun { int type, begin, end, pad; };
 
 template <typename R> struct DCam {
     R pixel_size, half_width, half_height, aperture, focal_length;
@@ -101,12 +131,15 @@ template <typename R> struct DCam {
 struct DTex { const uchar4* data; int w, h, layers; };
 
 template <typename R> struct Params {
-    const DObj<R>* objects;     int n_objects;
+    DObjHot<R> hot[kMaxObjects];
+    DRun runs[kMaxObjects];     int n_runs;
+    const DObjShade<R>* shade;  int n_objects;
     const V4<R>* node_lo;       // (min.xyz, -)
     const V4<R>* node_hi;       // (max.xyz, -)
     const int4* node_meta;      // (tri_begin, tri_count, skip, -)
     const V4<R>* tri_test;      // 3 per triangle: (p1.xyz,e1.x) (e1.yz,e2.xy) (e2.z,-,-,-)
     const V4<R>* tri_shade;     // 3 per triangle: (n1.xyz,col.r) (n2.xyz,col.g) (n3.xyz,col.b)
+    const R* lens;              // 2 per sample: sunflower(samples, 2, n), tracer.cl:235-248 (NULL without DoF)
     DCam<R> cam;
     DTex tex[3];
     const double* seeds;        // full frame, row-major
@@ -172,35 +205,58 @@ template <typename R> __device__ __forceinline__ V3<R> xf_dir(const R* m, V3<R> 
     return {m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z, m[8] * d.x + m[9] * d.y + m[10] * d.z};
 }
 
-// tracer.cl:250-268 checkAxis
-template <typename R> __device__ __forceinline__ void check_axis(R origin, R direction, R lo, R hi, R eps, R& tmin, R& tmax) {
-    R a = lo - origin, b = hi - origin;
-    R t0, t1;
-    if (m_abs(direction) >= eps) { t0 = a / direction; t1 = b / direction; }
-    else { t0 = a * m_huge<R>(); t1 = b * m_huge<R>(); }
+// Per-ray slab set-up for tracer.cl:250-268 checkAxis: t = (bound - origin) / direction when
+// |direction| >= EPSILON, else (bound - origin) * HUGE_VAL.  Both cases are "(bound - origin) * k"
+// with k = 1/direction or +inf, so k is computed once per ray and object instead of per box.
+// (double keeps the true division for last-bit agreement with the reference arithmetic.)
+template <typename R> struct Slab { R kx, ky, kz; bool dx, dy, dz; };
+__device__ __forceinline__ Slab<float> make_slab(V3<float> d, float eps) {
+    Slab<float> s;
+    s.dx = m_abs(d.x) >= eps; s.dy = m_abs(d.y) >= eps; s.dz = m_abs(d.z) >= eps;
+    s.kx = s.dx ? m_rcp(d.x) : m_huge<float>();
+    s.ky = s.dy ? m_rcp(d.y) : m_huge<float>();
+    s.kz = s.dz ? m_rcp(d.z) : m_huge<float>();
+    return s;
+}
+__device__ __forceinline__ Slab<double> make_slab(V3<double> d, double eps) {
+    Slab<double> s;
+    s.dx = m_abs(d.x) >= eps; s.dy = m_abs(d.y) >= eps; s.dz = m_abs(d.z) >= eps;
+    s.kx = s.ky = s.kz = m_huge<double>();
+    return s;
+}
+__device__ __forceinline__ void axis_t(float o, float, float k, bool, float lo, float hi, float& tmin, float& tmax) {
+    float t0 = (lo - o) * k, t1 = (hi - o) * k;
     bool sw = t0 > t1;
-    tmin = sw ? t1 : t0;
-    tmax = sw ? t0 : t1;
+    tmin = sw ? t1 : t0; tmax = sw ? t0 : t1;
+}
+__device__ __forceinline__ void axis_t(double o, double d, double k, bool big, double lo, double hi, double& tmin, double& tmax) {
+    double a = lo - o, b = hi - o;
+    double t0 = big ? a / d : a * k, t1 = big ? b / d : b * k;
+    bool sw = t0 > t1;
+    tmin = sw ? t1 : t0; tmax = sw ? t0 : t1;
 }
 // tracer.cl:270-280 intersectRayWithBox
-template <typename R> __device__ __forceinline__ bool ray_box(V3<R> o, V3<R> d, R lx, R ly, R lz, R hx, R hy, R hz, R eps) {
+template <typename R>
+__device__ __forceinline__ bool ray_box(V3<R> o, V3<R> d, const Slab<R>& s, R lx, R ly, R lz, R hx, R hy, R hz, R& tmin, R& tmax) {
     R x0, x1, y0, y1, z0, z1;
-    check_axis(o.x, d.x, lx, hx, eps, x0, x1);
-    check_axis(o.y, d.y, ly, hy, eps, y0, y1);
-    check_axis(o.z, d.z, lz, hz, eps, z0, z1);
-    return m_max(m_max(x0, y0), z0) < m_min(m_min(x1, y1), z1);
+    axis_t(o.x, d.x, s.kx, s.dx, lx, hx, x0, x1);
+    axis_t(o.y, d.y, s.ky, s.dy, ly, hy, y0, y1);
+    axis_t(o.z, d.z, s.kz, s.dz, lz, hz, z0, z1);
+    tmin = m_max(m_max(x0, y0), z0);
+    tmax = m_min(m_min(x1, y1), z1);
+    return tmin < tmax;
 }
 
 // tracer.cl:485-505
 template <typename R> __device__ __forceinline__ R schlick(V3<R> eye, V3<R> n, R n1, R n2) {
     R c = dot(eye, n);
     if (n1 > n2) {
-        R r = n1 / n2;
+        R r = m_div(n1, n2);
         R sin2 = (r * r) * (R(1) - c * c);
         if (sin2 > R(1)) return R(1);
         c = m_sqrt(R(1) - sin2);
     }
-    R t = (n1 - n2) / (n1 + n2);
+    R t = m_div(n1 - n2, n1 + n2);
     R r0 = t * t;
     R k = R(1) - c;
     R k2 = k * k;
@@ -208,7 +264,7 @@ template <typename R> __device__ __forceinline__ R schlick(V3<R> eye, V3<R> n, R
 }
 // tracer.cl:507-533
 template <typename R> __device__ __forceinline__ V3<R> refracted(V3<R> eye, V3<R> n, R n1, R n2) {
-    R ratio = n1 / n2;
+    R ratio = m_div(n1, n2);
     R cos_i = dot(eye, n);
     R sin2 = (ratio * ratio) * (R(1) - cos_i * cos_i);
     if (sin2 > R(1)) return {R(0), R(0), R(0)};
@@ -245,28 +301,35 @@ template <typename R> __device__ __forceinline__ void offer(Hit<R>& h, R t, int 
 
 // Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.
 template <typename R>
-__device__ __forceinline__ void closest_hit(const Params<R>& P, const DObj<R>* __restrict__ objs, V3<R> ro, V3<R> rd, Hit<R>& h) {
+__device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> rd, Hit<R>& h) {
     const R eps = P.eps;
     h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
-    for (int j = 0; j < P.n_objects; ++j) {
-        const DObj<R>& ob = objs[j];
-        const int type = ob.type;
-        if (type == 0) {                                         // plane, tracer.cl:478-483
+    for (int r = 0; r < P.n_runs; ++r) {
+      const int type = P.runs[r].type, jb = P.runs[r].begin, je = P.runs[r].end;
+      if (type == 0) {
+        for (int j = jb; j < je; ++j) {                          // plane, tracer.cl:478-483
+            const DObjHot<R>& ob = P.hot[j];
             R oy = ob.inv[4] * ro.x + ob.inv[5] * ro.y + ob.inv[6] * ro.z + ob.inv[7];
             R dy = ob.inv[4] * rd.x + ob.inv[5] * rd.y + ob.inv[6] * rd.z;
-            if (m_abs(dy) > eps) offer(h, -oy / dy, j, eps);
-        } else if (type == 1) {                                  // sphere, tracer.cl:448-476
+            R t = m_div(-oy, dy);
+            if (m_abs(dy) > eps) offer(h, t, j, eps);
+        }
+      } else if (type == 1) {
+        for (int j = jb; j < je; ++j) {                          // sphere, tracer.cl:448-476
+            const DObjHot<R>& ob = P.hot[j];
             V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
             R a = dot(d, d);
             R b = R(2) * dot(d, o);
             R c = dot(o, o) - R(1);
             R disc = b * b - R(4) * a * c;
-            if (disc > R(0)) {
-                R sq = m_sqrt(disc), den = R(2) * a;
-                offer(h, (-b - sq) / den, j, eps);
-                offer(h, (-b + sq) / den, j, eps);
-            }
-        } else if (type == 2) {                                  // cylinder side, caps off, tracer.cl:396-446
+            // branch-free: a negative discriminant gives NaN roots, which no comparison accepts
+            R sq = m_sqrt(disc), inv_den = m_rcp(R(2) * a);
+            R t1 = (-b - sq) * inv_den, t2 = (-b + sq) * inv_den;
+            if (disc > R(0)) { offer(h, t1, j, eps); offer(h, t2, j, eps); }
+        }
+      } else if (type == 2) {
+        for (int j = jb; j < je; ++j) {                          // cylinder side, caps off, tracer.cl:396-446
+            const DObjHot<R>& ob = P.hot[j];
             V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
             R a = d.x * d.x + d.z * d.z;
             if (!(m_abs(a) < eps)) {
@@ -274,30 +337,36 @@ __device__ __forceinline__ void closest_hit(const Params<R>& P, const DObj<R>* _
                 R c = o.x * o.x + o.z * o.z - R(1);
                 R disc = b * b - R(4) * a * c;
                 if (!(disc < R(0))) {
-                    R sq = m_sqrt(disc), den = R(2) * a;
-                    R t0 = (-b - sq) / den, t1 = (-b + sq) / den;
+                    R sq = m_sqrt(disc), inv_den = m_rcp(R(2) * a);
+                    R t0 = (-b - sq) * inv_den, t1 = (-b + sq) * inv_den;
                     R y0 = o.y + t0 * d.y, y1 = o.y + t1 * d.y;
-                    if (y0 > ob.min_y && y0 < ob.max_y) offer(h, t0, j, eps);
-                    if (y1 > ob.min_y && y1 < ob.max_y) offer(h, t1, j, eps);
+                    if (y0 > ob.aux[0] && y0 < ob.aux[1]) offer(h, t0, j, eps);
+                    if (y1 > ob.aux[0] && y1 < ob.aux[1]) offer(h, t1, j, eps);
                 }
             }
-        } else if (type == 3) {                                  // cube, tracer.cl:378-394
+        }
+      } else if (type == 3) {
+        for (int j = jb; j < je; ++j) {                          // cube, tracer.cl:378-394
+            const DObjHot<R>& ob = P.hot[j];
             V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            R x0, x1, y0, y1, z0, z1;
-            check_axis(o.x, d.x, R(-1), R(1), eps, x0, x1);
-            check_axis(o.y, d.y, R(-1), R(1), eps, y0, y1);
-            check_axis(o.z, d.z, R(-1), R(1), eps, z0, z1);
-            R tmin = m_max(m_max(x0, y0), z0), tmax = m_min(m_min(x1, y1), z1);
+            Slab<R> s = make_slab(d, eps);
+            R tmin, tmax;
+            ray_box(o, d, s, R(-1), R(-1), R(-1), R(1), R(1), R(1), tmin, tmax);
             if (!(tmin > tmax)) { offer(h, tmin, j, eps); offer(h, tmax, j, eps); }
-        } else if (type == 4) {                                  // group: AABB, then BVH, tracer.cl:598-720
+        }
+      } else if (type == 4) {
+        for (int j = jb; j < je; ++j) {                          // group: AABB, then BVH, tracer.cl:598-720
+            const DObjHot<R>& ob = P.hot[j];
             V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            if (!ray_box(o, d, ob.bb_min[0], ob.bb_min[1], ob.bb_min[2], ob.bb_max[0], ob.bb_max[1], ob.bb_max[2], eps)) continue;
+            Slab<R> s = make_slab(d, eps);
+            R tmin, tmax;
+            if (!ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], tmin, tmax)) continue;
             int i = ob.node_begin;
             const int end = ob.node_end;
             while (i < end) {
                 const V4<R> lo = ldg4(&P.node_lo[i]), hi = ldg4(&P.node_hi[i]);
                 const int4 meta = __ldg(&P.node_meta[i]);
-                if (!ray_box(o, d, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, eps)) { i = meta.z; continue; }
+                if (!ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tmin, tmax)) { i = meta.z; continue; }
                 const int tend = meta.x + meta.y;
                 for (int n = meta.x; n < tend; ++n) {            // Moeller-Trumbore, tracer.cl:640-675
                     const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
@@ -306,11 +375,11 @@ __device__ __forceinline__ void closest_hit(const Params<R>& P, const DObj<R>* _
                     V3<R> dxe2 = cross(d, e2);
                     R det = dot(e1, dxe2);
                     if (m_abs(det) < eps) continue;
-                    R f = R(1) / det;
-                    V3<R> s = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
-                    R u = f * dot(s, dxe2);
+                    R f = m_rcp(det);
+                    V3<R> sv = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
+                    R u = f * dot(sv, dxe2);
                     if (u < R(0) || u > R(1)) continue;
-                    V3<R> sxe1 = cross(s, e1);
+                    V3<R> sxe1 = cross(sv, e1);
                     R v = f * dot(d, sxe1);
                     if (v < R(0) || (u + v) > R(1)) continue;
                     R t = f * dot(e2, sxe1);
@@ -319,34 +388,12 @@ __device__ __forceinline__ void closest_hit(const Params<R>& P, const DObj<R>* _
                 i = i + 1;
             }
         }
+      }
     }
-}
-
-// tracer.cl:221-248 sunflower(amountPoints, alpha=2, pointNumber, randomize=false)
-template <typename R> __device__ __forceinline__ void sunflower(int amount, int index, R pi, R& ox, R& oy) {
-    R idx = R(index), n = R(amount);
-    R b = m_round(R(2) * m_sqrt(n));
-    R phi = (m_sqrt(R(5)) + R(1)) / R(2);
-    R r = R(1);
-    if (idx <= (n - b)) r = m_sqrt(idx - R(0.5)) / m_sqrt(n - (b + R(1)) / R(2));   // NaN at index 0: kept
-    R theta = R(2) * pi * idx / (phi * phi);
-    R s, c;
-    m_sincos(theta, &s, &c);
-    ox = r * c;
-    oy = r * s;
 }
 
 template <typename R, int RNG>
 __global__ void __launch_bounds__(kBlockThreads) trace_kernel(const __grid_constant__ Params<R> P) {
-    __shared__ DObj<R> s_obj[kMaxObjects];
-    {   // stage the object records once per block (tracer.cl:846-849 does it per work-item)
-        const int words = P.n_objects * (int)(sizeof(DObj<R>) / 4);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.objects);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(s_obj);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-
     const int W = P.cam.width;
     const int tiles_x = (W + kTileW - 1) / kTileW;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -388,10 +435,9 @@ __global__ void __launch_bounds__(kBlockThreads) trace_kernel(const __grid_const
             V3<R> pixel = xf_point(P.cam.inv, in_view);
             ro = cam_origin;
             rd = normalize(pixel - ro);
-            if (P.cam.aperture != R(0)) {
+            if (P.lens != nullptr) {                                                          // aperture != 0
                 V3<R> pos = ro + rd * P.cam.focal_length;
-                R sx, sy;
-                sunflower<R>((int)samples, (int)n, pi, sx, sy);
+                R sx = ldg1(&P.lens[2 * n]), sy = ldg1(&P.lens[2 * n + 1]);                     // NaN at n == 0 when samples >= 3: kept
                 V3<R> no = {ro.x + sy * P.cam.aperture, ro.y + sx * P.cam.aperture, ro.z};   // x/y swap as upstream
                 rd = pos - no;                                                                // left unnormalised
                 ro = no;
@@ -402,46 +448,51 @@ __global__ void __launch_bounds__(kBlockThreads) trace_kernel(const __grid_const
         }
 
         Hit<R> h;
-        closest_hit<R>(P, s_obj, ro, rd, h);
+        closest_hit<R>(P, ro, rd, h);
 
         bool done = true;                        // a miss ends the path (re-tracing it cannot hit either)
         if (h.obj >= 0) {
-            const DObj<R>& ob = s_obj[h.obj];
+            const DObjShade<R>& ob = P.shade[h.obj];
             const int type = ob.type;
             V3<R> position = ro + rd * h.t;
             V3<R> eye = {-rd.x, -rd.y, -rd.z};
             V3<R> lp = {R(0), R(0), R(0)};
-            if (type != 4) lp = xf_point(ob.inv, position);
-            V3<R> on;
+            if (ob.flags & 4) lp = xf_point(ob.inv, position);                    // spheres, cylinders, cubes, textured planes
+            V3<R> nv;
             V3<R> tri_color = {R(0), R(0), R(0)};
-            if (type == 0) {                                                      // tracer.cl:906-914
-                if (ob.flags & 2) {
+            if (type == 0 && !(ob.flags & 2)) {
+                // plane without normal map: object normal (0,1,0) -> world normal is a constant of the
+                // object, normalize(inverseTranspose * (0,1,0)), precomputed on the host (tracer.cl:913, 953-955)
+                nv = {ob.plane_n[0], ob.plane_n[1], ob.plane_n[2]};
+            } else {
+                V3<R> on;
+                if (type == 0) {                                                  // tracer.cl:906-911
                     float3 c = sample_rgba8(P.tex[0], (float)(m_abs(lp.x) * ob.tex_sx_nm), (float)(m_abs(lp.z) * ob.tex_sy_nm), ob.tex_index_nm);
                     on = normalize(V3<R>{R(c.x), R(c.y), R(c.z)});
-                } else on = {R(0), R(1), R(0)};
-            } else if (type == 1) {
-                on = lp;                                                          // tracer.cl:919-920
-            } else if (type == 2) {                                               // tracer.cl:924-932
-                R dist = lp.x * lp.x + lp.z * lp.z;
-                if (dist < R(1) && lp.y >= ob.max_y - eps) on = {R(0), R(1), R(0)};
-                else if (dist < R(1) && lp.y <= ob.min_y + eps) on = {R(0), R(-1), R(0)};
-                else on = {lp.x, R(0), lp.z};
-            } else if (type == 3) {                                               // tracer.cl:938-946
-                R ax = m_abs(lp.x), ay = m_abs(lp.y), az = m_abs(lp.z);
-                R maxc = m_max(m_max(ax, ay), az);
-                if (maxc == ax) on = {lp.x, R(0), R(0)};
-                else if (maxc == ay) on = {R(0), lp.y, R(0)};
-                else on = {R(0), R(0), lp.z};
-            } else {                                                              // tracer.cl:669, 949
-                const V4<R> s0 = ldg4(&P.tri_shade[3 * h.tri]), s1 = ldg4(&P.tri_shade[3 * h.tri + 1]), s2 = ldg4(&P.tri_shade[3 * h.tri + 2]);
-                R w = R(1) - h.u - h.v;
-                on = {s1.x * h.u + s2.x * h.v + s0.x * w, s1.y * h.u + s2.y * h.v + s0.y * w, s1.z * h.u + s2.z * h.v + s0.z * w};
-                tri_color = {s0.w, s1.w, s2.w};
+                } else if (type == 1) {
+                    on = lp;                                                      // tracer.cl:919-920
+                } else if (type == 2) {                                           // tracer.cl:924-932
+                    R dist = lp.x * lp.x + lp.z * lp.z;
+                    if (dist < R(1) && lp.y >= ob.max_y - eps) on = {R(0), R(1), R(0)};
+                    else if (dist < R(1) && lp.y <= ob.min_y + eps) on = {R(0), R(-1), R(0)};
+                    else on = {lp.x, R(0), lp.z};
+                } else if (type == 3) {                                           // tracer.cl:938-946
+                    R ax = m_abs(lp.x), ay = m_abs(lp.y), az = m_abs(lp.z);
+                    R maxc = m_max(m_max(ax, ay), az);
+                    if (maxc == ax) on = {lp.x, R(0), R(0)};
+                    else if (maxc == ay) on = {R(0), lp.y, R(0)};
+                    else on = {R(0), R(0), lp.z};
+                } else {                                                          // tracer.cl:669, 949
+                    const V4<R> s0 = ldg4(&P.tri_shade[3 * h.tri]), s1 = ldg4(&P.tri_shade[3 * h.tri + 1]), s2 = ldg4(&P.tri_shade[3 * h.tri + 2]);
+                    R w = R(1) - h.u - h.v;
+                    on = {s1.x * h.u + s2.x * h.v + s0.x * w, s1.y * h.u + s2.y * h.v + s0.y * w, s1.z * h.u + s2.z * h.v + s0.z * w};
+                    tri_color = {s0.w, s1.w, s2.w};
+                }
+                nv = {ob.invt[0] * on.x + ob.invt[1] * on.y + ob.invt[2] * on.z,
+                      ob.invt[3] * on.x + ob.invt[4] * on.y + ob.invt[5] * on.z,
+                      ob.invt[6] * on.x + ob.invt[7] * on.y + ob.invt[8] * on.z};   // tracer.cl:953-955
+                nv = normalize(nv);
             }
-            V3<R> nv = {ob.invt[0] * on.x + ob.invt[1] * on.y + ob.invt[2] * on.z,
-                        ob.invt[3] * on.x + ob.invt[4] * on.y + ob.invt[5] * on.z,
-                        ob.invt[6] * on.x + ob.invt[7] * on.y + ob.invt[8] * on.z};     // tracer.cl:953-955
-            nv = normalize(nv);
             if (dot(eye, nv) < R(0)) nv = nv * R(-1);                                  // tracer.cl:962-964
             V3<R> over = position + nv * eps;
             const V3<R> under = position - nv * eps;
@@ -469,11 +520,14 @@ __global__ void __launch_bounds__(kBlockThreads) trace_kernel(const __grid_const
                 R rand1 = R(2) * pi * R(noise3d<RNG>(fgi, (float)b, (float)n));
                 R rand2 = R(noise3d<RNG>((float)b, (float)n, fgi));
                 R rand2s = m_sqrt(rand2);
-                V3<R> axis = (m_abs(nv.x) > R(0.1)) ? V3<R>{R(0), R(1), R(0)} : V3<R>{R(1), R(0), R(0)};
-                V3<R> uu = normalize(cross(axis, nv));
+                // u = normalize(cross(axis, n)) with axis = (0,1,0) if |n.x| > 0.1 else (1,0,0); the cross
+                // product with a unit axis is written out (same values: the other terms are exact zeros)
+                const bool ay_axis = m_abs(nv.x) > R(0.1);
+                V3<R> uu = ay_axis ? V3<R>{nv.z, R(0), -nv.x} : V3<R>{R(0), -nv.z, nv.y};
+                uu = normalize(uu);
                 V3<R> vv = cross(nv, uu);
                 R s1, c1;
-                m_sincos(rand1, &s1, &c1);
+                m_sincos_2pi(rand1, &s1, &c1);
                 rd = uu * (c1 * rand2s) + vv * (s1 * rand2s) + nv * m_sqrt(R(1) - rand2);
                 cosine = dot(rd, nv);
             }
@@ -496,7 +550,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_kernel(const __grid_const
                         colr = {R(c.x), R(c.y), R(c.z)};
                     } else if (type == 1) {                                           // sphericalMap, tracer.cl:178-213
                         R theta = m_atan2(lp.x, lp.z);
-                        R radius = m_sqrt(dot(lp, lp));
+                        R radius = sqrt(dot(lp, lp));
                         R phi = m_acos(lp.y / radius);
                         R su = R(1) - (theta / (R(2) * pi) + R(0.5));
                         R sv = R(1) - phi / pi;

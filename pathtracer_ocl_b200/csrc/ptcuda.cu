@@ -52,7 +52,11 @@ void set_err(char* err, int errlen, const char* msg) {
 
 // ---- flattened scene (host copy), templated on the arithmetic type -----------------------------
 template <typename R> struct HostScene {
-    std::vector<ptk::DObj<R>> objects;
+    ptk::DObjHot<R> hot[ptk::kMaxObjects];
+    ptk::DRun runs[ptk::kMaxObjects];
+    int n_runs = 0;
+    std::vector<ptk::DObjShade<R>> shade;
+    std::vector<R> lens;       // sunflower lens points, 2 per sample (empty without depth of field)
     std::vector<ptk::V4<R>> node_lo, node_hi;
     std::vector<int4> node_meta;
     std::vector<ptk::V4<R>> tri_test, tri_shade;
@@ -95,38 +99,70 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
     const auto* objs = static_cast<const ptw_object*>(job.objects);
     const auto* tris = static_cast<const ptw_triangle*>(job.triangles);
     const auto* groups = static_cast<const ptw_group*>(job.groups);
+    std::memset(out.hot, 0, sizeof out.hot);
     for (int i = 0; i < job.n_objects; ++i) {
         const ptw_object& s = objs[i];
-        ptk::DObj<R> o;
+        ptk::DObjHot<R>& h = out.hot[i];
+        ptk::DObjShade<R> o;
         std::memset(&o, 0, sizeof o);
-        for (int k = 0; k < 12; ++k) o.inv[k] = R(s.inverse[k]);
+        for (int k = 0; k < 12; ++k) o.inv[k] = h.inv[k] = R(s.inverse[k]);
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) o.invt[r * 3 + c] = R(s.inverse_transpose[r * 4 + c]);
-        for (int k = 0; k < 3; ++k) {
-            o.color[k] = R(s.color[k]); o.emission[k] = R(s.emission[k]);
-            o.bb_min[k] = R(s.bb_min[k]); o.bb_max[k] = R(s.bb_max[k]);
-        }
+        for (int k = 0; k < 3; ++k) { o.color[k] = R(s.color[k]); o.emission[k] = R(s.emission[k]); }
         o.refractive_index = R(s.refractive_index); o.reflectivity = R(s.reflectivity);
         o.min_y = R(s.min_y); o.max_y = R(s.max_y);
         o.tex_sx = R(s.texture_scale_x); o.tex_sy = R(s.texture_scale_y);
         o.tex_sx_nm = R(s.texture_scale_x_nm); o.tex_sy_nm = R(s.texture_scale_y_nm);
-        o.type = (s.type >= 0 && s.type <= 4) ? int(s.type) : 999;
+        o.type = h.type = (s.type >= 0 && s.type <= 4) ? int(s.type) : 999;
         o.flags = (s.is_textured ? 1 : 0) | (s.is_textured_nm ? 2 : 0);
+        if ((o.type >= 1 && o.type <= 3) || o.flags != 0) o.flags |= 4;      // needs the object-space hit point
         o.tex_index = s.texture_index; o.tex_index_nm = s.texture_index_nm;
-        o.node_begin = o.node_end = int(out.node_lo.size());
-        if (o.type == 4 && s.child_count > 0) {
-            if (s.child_count > PTW_MAX_ROOT_CHILDREN) fail("object %d: child_count %d > %d", i, s.child_count, PTW_MAX_ROOT_CHILDREN);
-            if (!groups || job.n_groups <= 0) fail("object %d is a group but no BVH groups were passed", i);
-            for (int c = 0; c < s.child_count; ++c) emit_subtree<R>(groups, job.n_groups, tris, job.n_triangles, s.children[c], 0, out);
-            o.node_end = int(out.node_lo.size());
+        {   // world normal of an un-normal-mapped plane: normalize(inverseTranspose * (0,1,0,0)).xyz
+            const double nx = s.inverse_transpose[1], ny = s.inverse_transpose[5], nz = s.inverse_transpose[9];
+            const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+            o.plane_n[0] = R(nx / len); o.plane_n[1] = R(ny / len); o.plane_n[2] = R(nz / len);
         }
-        out.objects.push_back(o);
+        h.node_begin = h.node_end = int(out.node_lo.size());
+        if (h.type == 2) { h.aux[0] = R(s.min_y); h.aux[1] = R(s.max_y); }
+        if (h.type == 4) {
+            for (int k = 0; k < 3; ++k) { h.aux[k] = R(s.bb_min[k]); h.aux[3 + k] = R(s.bb_max[k]); }
+            if (s.child_count > 0) {
+                if (s.child_count > PTW_MAX_ROOT_CHILDREN) fail("object %d: child_count %d > %d", i, s.child_count, PTW_MAX_ROOT_CHILDREN);
+                if (!groups || job.n_groups <= 0) fail("object %d is a group but no BVH groups were passed", i);
+                for (int c = 0; c < s.child_count; ++c) emit_subtree<R>(groups, job.n_groups, tris, job.n_triangles, s.children[c], 0, out);
+                h.node_end = int(out.node_lo.size());
+            }
+        }
+        out.shade.push_back(o);
+    }
+    // runs of consecutive same-type objects (order preserved)
+    out.n_runs = 0;
+    for (int i = 0; i < job.n_objects; ++i) {
+        if (out.n_runs > 0 && out.runs[out.n_runs - 1].type == out.hot[i].type) { out.runs[out.n_runs - 1].end = i + 1; continue; }
+        out.runs[out.n_runs++] = ptk::DRun{out.hot[i].type, i, i + 1, 0};
     }
     const auto* cam = static_cast<const ptw_camera*>(job.camera);
     out.cam.pixel_size = R(cam->pixel_size); out.cam.half_width = R(cam->half_width); out.cam.half_height = R(cam->half_height);
     out.cam.aperture = R(cam->aperture); out.cam.focal_length = R(cam->focal_length);
     for (int k = 0; k < 12; ++k) out.cam.inv[k] = R(cam->inverse[k]);
     out.cam.width = cam->width; out.cam.height = cam->height;
+    if (cam->aperture != 0.0) {
+        // tracer.cl:221-248 sunflower(amountPoints = samples, alpha = 2, pointNumber = n, randomize = false):
+        // a function of the sample index only, evaluated here in double once instead of per path.
+        const double PI = double(3.14159265359f);
+        const double amount = double(job.samples);
+        const double b = std::round(2.0 * std::sqrt(amount));
+        const double phi = (std::sqrt(5.0) + 1.0) / 2.0;
+        out.lens.resize(size_t(job.samples) * 2);
+        for (int n = 0; n < job.samples; ++n) {
+            const double idx = double(n);
+            double r = 1.0;
+            if (idx <= (amount - b)) r = std::sqrt(idx - 0.5) / std::sqrt(amount - (b + 1.0) / 2.0);   // NaN at n == 0: kept
+            const double theta = 2.0 * PI * idx / (phi * phi);
+            out.lens[size_t(n) * 2] = R(r * std::cos(theta));
+            out.lens[size_t(n) * 2 + 1] = R(r * std::sin(theta));
+        }
+    }
 }
 
 struct DeviceState {
@@ -135,7 +171,7 @@ struct DeviceState {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<int> rows;          // frame rows owned by this device, increasing
     std::vector<void*> allocs;      // everything cudaMalloc'ed on this device
-    void* objects = nullptr; void* node_lo = nullptr; void* node_hi = nullptr; void* node_meta = nullptr;
+    void* shade = nullptr; void* lens = nullptr; void* node_lo = nullptr; void* node_hi = nullptr; void* node_meta = nullptr;
     void* tri_test = nullptr; void* tri_shade = nullptr;
     void* tex[3] = {nullptr, nullptr, nullptr};
     double* seeds = nullptr;
@@ -181,7 +217,8 @@ template <typename T> void* upload(DeviceState& d, const std::vector<T>& v, int6
 }
 
 template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const HostScene<R>& s, int64_t& h2d) {
-    d.objects = upload(d, s.objects, h2d);
+    d.shade = upload(d, s.shade, h2d);
+    d.lens = s.lens.empty() ? nullptr : upload(d, s.lens, h2d);
     d.node_lo = upload(d, s.node_lo, h2d);
     d.node_hi = upload(d, s.node_hi, h2d);
     d.node_meta = upload(d, s.node_meta, h2d);
@@ -193,7 +230,11 @@ template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const Ho
 template <typename R> ptk::Params<R> make_params(const ptc_context& c, const DeviceState& d, const HostScene<R>& s) {
     ptk::Params<R> P;
     std::memset(&P, 0, sizeof P);
-    P.objects = static_cast<const ptk::DObj<R>*>(d.objects);
+    std::memcpy(P.hot, s.hot, sizeof P.hot);
+    std::memcpy(P.runs, s.runs, sizeof P.runs);
+    P.n_runs = s.n_runs;
+    P.shade = static_cast<const ptk::DObjShade<R>*>(d.shade);
+    P.lens = static_cast<const R*>(d.lens);
     P.n_objects = c.n_objects;
     P.node_lo = static_cast<const ptk::V4<R>*>(d.node_lo);
     P.node_hi = static_cast<const ptk::V4<R>*>(d.node_hi);

@@ -13,13 +13,13 @@ from pathtracer_ocl_b200 import scene as S, trace as T  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
-def parity(name, W, H, spp, ap=0.0, fl=0.0, tex_scale=8):
+def parity(name, W, H, spp, ap=0.0, fl=0.0, tex_scale=8, rng=0):
     sc = S.build_scene(name, W, H, ap, fl, tex_scale=tex_scale)
     seeds = S.make_seeds(0x5EED0000 + spp, W * H)
-    ref, cnt = O.trace(sc, seeds, spp, precision=1)
+    ref, cnt = O.trace(sc, seeds, spp, precision=1, rng_mode=rng)
     out = {}
     for prec, tol in ((T.FP64, 1e-6), (T.FP32, 1e-3)):
-        img = T.render_scene(sc, spp, seeds, precision=prec)
+        img = T.render_scene(sc, spp, seeds, precision=prec, rng_mode=rng)
         err = np.abs(img[..., :3] - ref[..., :3]).max(axis=-1)
         out["fp64" if prec else "fp32"] = dict(frac=float((err <= tol).mean()), max=float(err.max()),
                                                nan=int(np.isnan(img).sum()))
@@ -49,6 +49,8 @@ if __name__ == "__main__":
     dev = T.debug_noise3d(x)
     print("noise3d bit-exact:", bool((ref.view(np.uint32) == dev.view(np.uint32)).all()), "mismatches", int((ref != dev).sum()))
     parity("default", 320, 240, 1)
+    parity("default", 320, 240, 1, rng=1)
+    parity("teapot", 160, 120, 1, rng=1)
     parity("reference", 320, 240, 1, 0.15, 1.6)
     parity("reference", 160, 120, 16, 0.15, 1.6)
     parity("transparency", 320, 240, 2)
