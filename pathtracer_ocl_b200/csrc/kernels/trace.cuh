@@ -37,8 +37,20 @@
 
 namespace ptk {
 
+// Resident-blocks hints for the register allocator, tuned by measurement on B200 (profiles/):
+// fp32 runs best at 6 blocks x 128 threads (72 registers), fp64 needs more registers per thread.
+#ifndef PTK_MIN_BLOCKS
+#define PTK_MIN_BLOCKS 6
+#endif
+#ifndef PTK_MIN_BLOCKS_F64
+#define PTK_MIN_BLOCKS_F64 3
+#endif
+#ifndef PTK_BLOCK_THREADS
+#define PTK_BLOCK_THREADS 128
+#endif
+
 constexpr int kMaxObjects = 16;
-constexpr int kBlockThreads = 128;
+constexpr int kBlockThreads = PTK_BLOCK_THREADS;
 constexpr int kTileW = 8, kTileH = 4;   // pixels covered by one warp
 
 template <typename R> struct alignas(16) V4 { R x, y, z, w; };
@@ -299,6 +311,16 @@ template <typename R> __device__ __forceinline__ void offer(Hit<R>& h, R t, int 
     if (t > eps && t < h.t) { h.t = t; h.obj = obj; }
 }
 
+// Roots of the sphere quadratic, tracer.cl:465-475: recorded only when the discriminant is strictly
+// positive.  Branch-free: a non-positive discriminant turns the roots into NaN, which offer() rejects.
+template <typename R> __device__ __forceinline__ void sphere_roots(Hit<R>& h, R a, R b, R disc, int j, R eps) {
+    R sq = m_sqrt(disc);
+    sq = disc > R(0) ? sq : m_huge<R>() * R(0);
+    R inv_den = m_rcp(R(2) * a);
+    offer(h, (-b - sq) * inv_den, j, eps);
+    offer(h, (-b + sq) * inv_den, j, eps);
+}
+
 // Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.
 template <typename R>
 __device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> rd, Hit<R>& h) {
@@ -322,10 +344,18 @@ __device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> 
             R b = R(2) * dot(d, o);
             R c = dot(o, o) - R(1);
             R disc = b * b - R(4) * a * c;
-            // branch-free: a negative discriminant gives NaN roots, which no comparison accepts
-            R sq = m_sqrt(disc), inv_den = m_rcp(R(2) * a);
-            R t1 = (-b - sq) * inv_den, t2 = (-b + sq) * inv_den;
-            if (disc > R(0)) { offer(h, t1, j, eps); offer(h, t2, j, eps); }
+            sphere_roots(h, a, b, disc, j, eps);
+        }
+      } else if (type == 5) {
+        for (int j = jb; j < je; ++j) {                          // sphere whose inverse is scale+translate only
+            const DObjHot<R>& ob = P.hot[j];                     // (the off-diagonal terms are exact zeros)
+            V3<R> o = {ob.inv[0] * ro.x + ob.inv[3], ob.inv[5] * ro.y + ob.inv[7], ob.inv[10] * ro.z + ob.inv[11]};
+            V3<R> d = {ob.inv[0] * rd.x, ob.inv[5] * rd.y, ob.inv[10] * rd.z};
+            R a = dot(d, d);
+            R b = R(2) * dot(d, o);
+            R c = dot(o, o) - R(1);
+            R disc = b * b - R(4) * a * c;
+            sphere_roots(h, a, b, disc, j, eps);
         }
       } else if (type == 2) {
         for (int j = jb; j < je; ++j) {                          // cylinder side, caps off, tracer.cl:396-446
@@ -393,7 +423,7 @@ __device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> 
 }
 
 template <typename R, int RNG>
-__global__ void __launch_bounds__(kBlockThreads) trace_kernel(const __grid_constant__ Params<R> P) {
+__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS)) trace_kernel(const __grid_constant__ Params<R> P) {
     const int W = P.cam.width;
     const int tiles_x = (W + kTileW - 1) / kTileW;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

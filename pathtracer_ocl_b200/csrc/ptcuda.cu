@@ -124,6 +124,9 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
         }
         h.node_begin = h.node_end = int(out.node_lo.size());
         if (h.type == 2) { h.aux[0] = R(s.min_y); h.aux[1] = R(s.max_y); }
+        if (h.type == 1 && s.inverse[1] == 0.0 && s.inverse[2] == 0.0 && s.inverse[4] == 0.0 && s.inverse[6] == 0.0 &&
+            s.inverse[8] == 0.0 && s.inverse[9] == 0.0)
+            h.type = 5;                                         // intersection-loop fast path; o.type stays 1 for shading
         if (h.type == 4) {
             for (int k = 0; k < 3; ++k) { h.aux[k] = R(s.bb_min[k]); h.aux[3 + k] = R(s.bb_max[k]); }
             if (s.child_count > 0) {

@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libptcuda.so")
+_LIB_PATH = os.environ.get("PTCUDA_LIB") or os.path.join(_HERE, "libptcuda.so")   # override: kernel A/B experiments
 
 PTC_ABI_VERSION = 1
 FP32, FP64 = 0, 1
