@@ -321,9 +321,96 @@ template <typename R> __device__ __forceinline__ void sphere_roots(Hit<R>& h, R 
     offer(h, (-b + sq) * inv_den, j, eps);
 }
 
-// Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.
+// ---- warp-cooperative BVH walk -------------------------------------------------------------------
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <typename R> __device__ __forceinline__ V3<R> shfl3(V3<R> v, int src) {
+    return {__shfl_sync(kFullMask, v.x, src), __shfl_sync(kFullMask, v.y, src), __shfl_sync(kFullMask, v.z, src)};
+}
+// Smallest t over the warp (t > 0 or +inf): one REDUX on the bit pattern for fp32, a shuffle tree for fp64.
+__device__ __forceinline__ float warp_min_pos(float t) { return __uint_as_float(__reduce_min_sync(kFullMask, __float_as_uint(t))); }
+__device__ __forceinline__ double warp_min_pos(double t) {
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) t = fmin(t, __shfl_xor_sync(kFullMask, t, k));
+    return t;
+}
+
+// One group object (tracer.cl:598-720): object AABB, then the BVH below its root children.
+//
+// The reference walks the tree per work-item and tests every triangle of every node whose box the
+// ray hits; inner nodes of the Go-built BVH hold up to hundreds of triangles, so per-lane triangle
+// loops diverge badly (one lane inside the mesh stalls 31 others).  Here the work is split by kind:
+//   * each lane walks the node list for its OWN ray -- box tests only, one node per step, in the
+//     reference's visiting order (the pre-order list with skip links needs no stack);
+//   * when a lane reaches a node that holds triangles it posts it, and the warp drains the posted
+//     nodes one at a time: the ray is broadcast and the 32 lanes test 32 consecutive triangles at
+//     once, then a warp arg-min (smallest t > EPSILON, ties to the lowest triangle index = the one
+//     the reference would have recorded first) hands the result back to the owning lane.
+// Nodes whose box lies entirely beyond the lane's closest hit so far, or entirely behind the ray,
+// cannot contain the winner (a triangle's hit point lies inside its node's box) and are skipped
+// with their subtree -- a pure cull, the result is the reference's.
 template <typename R>
-__device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> rd, Hit<R>& h) {
+__device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& ob, int j, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h) {
+    const R eps = P.eps;
+    const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+    const Slab<R> s = make_slab(d, eps);
+    R tmin, tmax;
+    bool walking = live && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], tmin, tmax);
+    int i = ob.node_begin;
+    const int node_end = ob.node_end;
+    while (__any_sync(kFullMask, walking)) {
+        bool post = false;
+        int tb = 0, te = 0;
+        if (walking) {
+            if (i >= node_end) walking = false;
+            else {
+                const V4<R> lo = ldg4(&P.node_lo[i]), hi = ldg4(&P.node_hi[i]);
+                const int4 meta = __ldg(&P.node_meta[i]);
+                const bool hitbox = ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tmin, tmax);
+                if (!hitbox || tmin > h.t * R(1.0001) || tmax < -eps) i = meta.z;
+                else { i = i + 1; tb = meta.x; te = meta.x + meta.y; post = meta.y > 0; }
+            }
+        }
+        unsigned pending = __ballot_sync(kFullMask, post);
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const V3<R> bo = shfl3(o, leader), bd = shfl3(d, leader);
+            const int btb = __shfl_sync(kFullMask, tb, leader), bte = __shfl_sync(kFullMask, te, leader);
+            R ct = m_huge<R>(), cu = R(0), cv = R(0);                // this lane's best candidate in the node
+            int ctri = 0x7fffffff;
+            for (int base = btb; base < bte; base += 32) {          // Moeller-Trumbore, tracer.cl:640-675
+                const int n = base + lane;
+                if (n < bte) {
+                    const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
+                    const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * n + 2].x)};
+                    const V3<R> e1 = {q0.w, q1.x, q1.y};
+                    const V3<R> dxe2 = cross(bd, e2);
+                    const R det = dot(e1, dxe2);
+                    const R f = m_rcp(det);
+                    const V3<R> sv = {bo.x - q0.x, bo.y - q0.y, bo.z - q0.z};
+                    const R u = f * dot(sv, dxe2);
+                    const V3<R> sxe1 = cross(sv, e1);
+                    const R v = f * dot(bd, sxe1);
+                    const R t = f * dot(e2, sxe1);
+                    const bool ok = !(m_abs(det) < eps) && !(u < R(0) || u > R(1)) && !(v < R(0) || (u + v) > R(1));
+                    if (ok && t > eps && t < ct) { ct = t; ctri = n; cu = u; cv = v; }
+                }
+            }
+            const R wt = warp_min_pos(ct);                            // warp arg-min: smallest t, then lowest index
+            if (wt < m_huge<R>()) {
+                const int wtri = __reduce_min_sync(kFullMask, (ct == wt) ? ctri : 0x7fffffff);
+                const int winner = __ffs(__ballot_sync(kFullMask, ctri == wtri)) - 1;
+                const R wu = __shfl_sync(kFullMask, cu, winner), wv = __shfl_sync(kFullMask, cv, winner);
+                if (lane == leader && wt < h.t) { h.t = wt; h.obj = j; h.tri = wtri; h.u = wu; h.v = wv; }
+            }
+        }
+    }
+}
+
+// Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.
+template <typename R, bool GROUPS>
+__device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h) {
     const R eps = P.eps;
     h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
     for (int r = 0; r < P.n_runs; ++r) {
@@ -384,45 +471,15 @@ __device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> 
             ray_box(o, d, s, R(-1), R(-1), R(-1), R(1), R(1), R(1), tmin, tmax);
             if (!(tmin > tmax)) { offer(h, tmin, j, eps); offer(h, tmax, j, eps); }
         }
-      } else if (type == 4) {
-        for (int j = jb; j < je; ++j) {                          // group: AABB, then BVH, tracer.cl:598-720
-            const DObjHot<R>& ob = P.hot[j];
-            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            Slab<R> s = make_slab(d, eps);
-            R tmin, tmax;
-            if (!ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], tmin, tmax)) continue;
-            int i = ob.node_begin;
-            const int end = ob.node_end;
-            while (i < end) {
-                const V4<R> lo = ldg4(&P.node_lo[i]), hi = ldg4(&P.node_hi[i]);
-                const int4 meta = __ldg(&P.node_meta[i]);
-                if (!ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tmin, tmax)) { i = meta.z; continue; }
-                const int tend = meta.x + meta.y;
-                for (int n = meta.x; n < tend; ++n) {            // Moeller-Trumbore, tracer.cl:640-675
-                    const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
-                    const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * n + 2].x)};
-                    const V3<R> e1 = {q0.w, q1.x, q1.y};
-                    V3<R> dxe2 = cross(d, e2);
-                    R det = dot(e1, dxe2);
-                    if (m_abs(det) < eps) continue;
-                    R f = m_rcp(det);
-                    V3<R> sv = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
-                    R u = f * dot(sv, dxe2);
-                    if (u < R(0) || u > R(1)) continue;
-                    V3<R> sxe1 = cross(sv, e1);
-                    R v = f * dot(d, sxe1);
-                    if (v < R(0) || (u + v) > R(1)) continue;
-                    R t = f * dot(e2, sxe1);
-                    if (t > eps && t < h.t) { h.t = t; h.obj = j; h.tri = n; h.u = u; h.v = v; }
-                }
-                i = i + 1;
-            }
-        }
+      } else if (GROUPS && type == 4) {
+        for (int j = jb; j < je; ++j) group_hit<R>(P, P.hot[j], j, ro, rd, live, lane, h);
       }
     }
 }
 
-template <typename R, int RNG>
+// GROUPS = the scene contains mesh objects: only then is the warp-cooperative walk compiled in and
+// the warp kept together until its last lane finishes.
+template <typename R, int RNG, bool GROUPS>
 __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS)) trace_kernel(const __grid_constant__ Params<R> P) {
     const int W = P.cam.width;
     const int tiles_x = (W + kTileW - 1) / kTileW;
@@ -430,13 +487,14 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     const int lane = threadIdx.x & 31;
     const int lx = (warp % tiles_x) * kTileW + (lane & (kTileW - 1));
     const int ly = (warp / tiles_x) * kTileH + (lane / kTileW);
-    if (lx >= W || ly >= P.rows) return;
-    const int gy = P.row_map[ly];
+    // Lanes without a pixel stay in the loop (idle): the BVH walk is warp-cooperative and uses all 32 lanes.
+    const bool has_pixel = lx < W && ly < P.rows;
+    const int gy = has_pixel ? P.row_map[ly] : 0;
     const int slice = blockIdx.y;
 
     const R eps = P.eps, pi = P.pi;
     const unsigned samples = (unsigned)P.samples;
-    const double seed = P.seeds[(size_t)gy * W + lx];
+    const double seed = has_pixel ? P.seeds[(size_t)gy * W + lx] : 0.0;
     const float fgi = (float)(seed / (double)P.n_objects);     // tracer.cl:840
     const float fgi2 = (float)(seed / (double)samples);        // tracer.cl:841
 
@@ -450,12 +508,15 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     unsigned b = 0, effective = 0;     // bounce counters (tracer.cl:873-884)
     bool inside = false;
     bool fresh = true;                 // need a new camera ray
+    bool live = has_pixel;             // false once this lane has finished all its samples
     V3<R> ro = {R(0), R(0), R(0)}, rd = {R(0), R(0), R(0)};
     V3<R> mask = {R(1), R(1), R(1)}, accum = {R(0), R(0), R(0)};
 
     while (true) {
-        if (fresh) {
-            if (n >= samples) break;
+        if (fresh && n >= samples) live = false;
+        if (GROUPS) { if (!__any_sync(kFullMask, live)) break; }   // the warp leaves together
+        else if (!live) break;
+        if (fresh && live) {
             // rayForPixel, tracer.cl:745-779
             float jx = noise3d<RNG>(fgi, (float)n, fgi2);
             float jy = noise3d<RNG>(fgi, fgi2, (float)n);
@@ -478,10 +539,10 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
         }
 
         Hit<R> h;
-        closest_hit<R>(P, ro, rd, h);
+        closest_hit<R, GROUPS>(P, ro, rd, live, lane, h);
 
-        bool done = true;                        // a miss ends the path (re-tracing it cannot hit either)
-        if (h.obj >= 0) {
+        bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
+        if (live && h.obj >= 0) {
             const DObjShade<R>& ob = P.shade[h.obj];
             const int type = ob.type;
             V3<R> position = ro + rd * h.t;
@@ -614,6 +675,7 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
         }
     }
 
+    if (!has_pixel) return;
     const size_t pix = (size_t)ly * W + lx;
     if (P.slices == 1) {
         const double wgt = 1.0 / (double)samples;                                    // tracer.cl:837, 1184-1187

@@ -267,8 +267,16 @@ template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScen
     const int warps_per_block = ptk::kBlockThreads / 32;
     dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
     dim3 block(ptk::kBlockThreads, 1, 1);
-    if (c.rng_mode == PTC_RNG_FAST) ptk::trace_kernel<R, ptk::RNG_FAST><<<grid, block, 0, d.stream>>>(P);
-    else ptk::trace_kernel<R, ptk::RNG_PARITY><<<grid, block, 0, d.stream>>>(P);
+    bool groups = false;
+    for (int i = 0; i < c.n_objects; ++i) groups = groups || (s.hot[i].type == 4 && s.hot[i].node_end > s.hot[i].node_begin);
+    const bool fast = c.rng_mode == PTC_RNG_FAST;
+    if (groups) {
+        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, true><<<grid, block, 0, d.stream>>>(P);
+        else ptk::trace_kernel<R, ptk::RNG_PARITY, true><<<grid, block, 0, d.stream>>>(P);
+    } else {
+        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, false><<<grid, block, 0, d.stream>>>(P);
+        else ptk::trace_kernel<R, ptk::RNG_PARITY, false><<<grid, block, 0, d.stream>>>(P);
+    }
     CUDA_OK(cudaGetLastError());
     c.stats.kernel_launches++;
     if (d.slices > 1) {
