@@ -1,0 +1,145 @@
+// Package cuda is the cgo binding that replaces internal/ocl's OpenCL driver in
+// eriklupander/pathtracer-ocl with libptcuda (hand-written sm_100a kernels behind a C ABI).
+//
+// It is a drop-in for the two things the rest of the Go program uses from internal/ocl:
+//
+//	ocl.Trace(objects, triangles, groups, deviceIndex, samples, camera, textures, sphereTextures, cubeTextures) []float64
+//	    (internal/ocl/ocltracer.go:100)  ->  cuda.Trace(... same arguments ...)
+//	listDevices()  (cmd/pt/main.go:98-112)  ->  cuda.ListDevices()
+//
+// The scene records (ocl.CLObject / CLTriangle / CLGroup / CLCamera) are passed through untouched:
+// libptcuda consumes the same packed bytes the OpenCL kernel did (include/ptwire.h).
+//
+// NOTE: this file was written without a Go toolchain (none exists in the build image); it has been
+// checked by eye against include/ptcuda.h only.  See INTEGRATION.md for the build line.
+package cuda
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../pathtracer_ocl_b200 -lptcuda -Wl,-rpath,${SRCDIR}/../../../pathtracer_ocl_b200
+#include <stdlib.h>
+#include <string.h>
+#include "ptcuda.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"image"
+	"math/rand"
+	"unsafe"
+
+	"github.com/eriklupander/pathtracer-ocl/internal/ocl"
+	"github.com/sirupsen/logrus"
+)
+
+// Options selects what the OpenCL path could not: arithmetic precision, RNG evaluation, several GPUs.
+type Options struct {
+	FP64    bool    // false: fp32 mode (default), true: fp64, the arithmetic of tracer.cl
+	FastRNG bool    // cheaper evaluation of the same noise3D hash (still reproducible)
+	Devices []int32 // GPUs driven by this process; nil = {deviceIndex}
+	Seeds   []float64
+}
+
+// ListDevices prints what the reference's --list-devices prints (cmd/pt/main.go:98-112).
+func ListDevices() {
+	n := int(C.ptc_device_count())
+	for i := 0; i < n; i++ {
+		buf := make([]byte, 256)
+		if C.ptc_device_name(C.int(i), (*C.char)(unsafe.Pointer(&buf[0])), C.int(len(buf))) == 0 {
+			fmt.Printf("Index: %d Type: GPU Name: %s\n", i, C.GoString((*C.char)(unsafe.Pointer(&buf[0]))))
+		}
+	}
+}
+
+// Trace has the signature of ocl.Trace (internal/ocl/ocltracer.go:100).
+func Trace(objects []ocl.CLObject, triangles []ocl.CLTriangle, groups []ocl.CLGroup, deviceIndex, samples int,
+	camera ocl.CLCamera, textures []image.Image, sphereTextures []image.Image, cubeTextures []image.Image) []float64 {
+	return TraceWithOptions(objects, triangles, groups, deviceIndex, samples, camera, textures, sphereTextures, cubeTextures, Options{})
+}
+
+// packTextures mirrors prepareTextures (ocltracer.go:228-254): same-sized *image.NRGBA packed back to back.
+func packTextures(imgs []image.Image) ([]byte, int, int, int) {
+	if len(imgs) == 0 {
+		return nil, 0, 0, 0
+	}
+	first := imgs[0].(*image.NRGBA)
+	w, h := first.Bounds().Dx(), first.Bounds().Dy()
+	all := make([]byte, 0, len(imgs)*w*h*4)
+	for _, im := range imgs {
+		n := im.(*image.NRGBA)
+		if n.Bounds().Dx() != w || n.Bounds().Dy() != h {
+			logrus.Fatalf("textures of one class must share a size")
+		}
+		if n.Stride == w*4 {
+			all = append(all, n.Pix[:w*h*4]...)
+		} else {
+			for y := 0; y < h; y++ {
+				all = append(all, n.Pix[y*n.Stride:y*n.Stride+w*4]...)
+			}
+		}
+	}
+	return all, w, h, len(imgs)
+}
+
+func TraceWithOptions(objects []ocl.CLObject, triangles []ocl.CLTriangle, groups []ocl.CLGroup, deviceIndex, samples int,
+	camera ocl.CLCamera, textures []image.Image, sphereTextures []image.Image, cubeTextures []image.Image, opt Options) []float64 {
+
+	numPixels := int(camera.Width * camera.Height)
+	logrus.Infof("trace with %d objects %dx%d", len(objects), camera.Width, camera.Height)
+
+	// one random double per pixel, as computeBatch does per batch (ocltracer.go:260-263)
+	seeds := opt.Seeds
+	if seeds == nil {
+		seeds = make([]float64, numPixels)
+		for i := range seeds {
+			seeds[i] = rand.Float64()
+		}
+	}
+
+	// Every buffer goes to C as a direct call argument (ptc_render_flat): cgo pins Go memory passed
+	// that way for the duration of the call, whereas storing Go pointers inside a C struct is not allowed.
+	var tex [3]*C.uint8_t
+	var texDims [9]C.int32_t
+	var keep [3][]byte
+	for cls, imgs := range [][]image.Image{textures, sphereTextures, cubeTextures} {
+		pix, w, h, layers := packTextures(imgs)
+		if layers == 0 {
+			continue
+		}
+		keep[cls] = pix
+		tex[cls] = (*C.uint8_t)(unsafe.Pointer(&pix[0]))
+		texDims[3*cls], texDims[3*cls+1], texDims[3*cls+2] = C.int32_t(w), C.int32_t(h), C.int32_t(layers)
+	}
+	var triPtr, grpPtr unsafe.Pointer
+	if len(triangles) > 0 {
+		triPtr = unsafe.Pointer(&triangles[0])
+	}
+	if len(groups) > 0 {
+		grpPtr = unsafe.Pointer(&groups[0])
+	}
+	precision, rngMode := C.int32_t(C.PTC_FP32), C.int32_t(C.PTC_RNG_PARITY)
+	if opt.FP64 {
+		precision = C.PTC_FP64
+	}
+	if opt.FastRNG {
+		rngMode = C.PTC_RNG_FAST
+	}
+	devices := opt.Devices
+	if devices == nil {
+		devices = []int32{int32(deviceIndex)}
+	}
+
+	results := make([]float64, numPixels*4)
+	errbuf := make([]byte, 512)
+	rc := C.ptc_render_flat(unsafe.Pointer(&objects[0]), C.int32_t(len(objects)), triPtr, C.int32_t(len(triangles)),
+		grpPtr, C.int32_t(len(groups)), unsafe.Pointer(&camera), tex[0], tex[1], tex[2], &texDims[0],
+		(*C.double)(unsafe.Pointer(&seeds[0])), C.int32_t(samples), precision, rngMode,
+		(*C.int32_t)(unsafe.Pointer(&devices[0])), C.int32_t(len(devices)),
+		(*C.double)(unsafe.Pointer(&results[0])), (*C.char)(unsafe.Pointer(&errbuf[0])), C.int(len(errbuf)))
+	if rc != 0 {
+		logrus.Fatalf("ptc_render failed: %s", C.GoString((*C.char)(unsafe.Pointer(&errbuf[0]))))
+	}
+	_ = keep
+	return results
+}

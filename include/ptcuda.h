@@ -112,6 +112,16 @@ int ptc_device_name(int index, char *buf, int buflen);
 /* One-shot drop-in for ocl.Trace().  out_rgba: rows_of_this_shard * width * 4 doubles. */
 int ptc_render(const ptc_job *job, double *out_rgba, char *err, int errlen);
 
+/* ptc_render with every buffer as a direct argument instead of through ptc_job: the form a cgo
+ * caller needs (Go may pass Go pointers as call arguments but may not store them inside a struct
+ * handed to C).  tex_dims = {w0,h0,layers0, w1,h1,layers1, w2,h2,layers2}; devices may be NULL. */
+int ptc_render_flat(const void *objects, int32_t n_objects, const void *triangles, int32_t n_triangles,
+                    const void *groups, int32_t n_groups, const void *camera,
+                    const uint8_t *tex_plane, const uint8_t *tex_sphere, const uint8_t *tex_cube,
+                    const int32_t *tex_dims, const double *seeds, int32_t samples, int32_t precision,
+                    int32_t rng_mode, const int32_t *devices, int32_t n_devices, double *out_rgba,
+                    char *err, int errlen);
+
 /* Phase API. */
 int  ptc_open(const ptc_job *job, ptc_context **ctx, char *err, int errlen);
 int  ptc_trace(ptc_context *ctx, char *err, int errlen);   /* launches + waits; result stays in HBM */

@@ -609,6 +609,27 @@ int ptc_render(const ptc_job* job, double* out_rgba, char* err, int errlen) {
     return rc;
 }
 
+int ptc_render_flat(const void* objects, int32_t n_objects, const void* triangles, int32_t n_triangles, const void* groups,
+                    int32_t n_groups, const void* camera, const uint8_t* tex_plane, const uint8_t* tex_sphere,
+                    const uint8_t* tex_cube, const int32_t* tex_dims, const double* seeds, int32_t samples, int32_t precision,
+                    int32_t rng_mode, const int32_t* devices, int32_t n_devices, double* out_rgba, char* err, int errlen) {
+    ptc_job job;
+    std::memset(&job, 0, sizeof job);
+    job.abi_version = PTC_ABI_VERSION;
+    job.objects = objects; job.n_objects = n_objects;
+    job.triangles = triangles; job.n_triangles = n_triangles;
+    job.groups = groups; job.n_groups = n_groups;
+    job.camera = camera;
+    const uint8_t* tex[3] = {tex_plane, tex_sphere, tex_cube};
+    for (int k = 0; k < 3; ++k) {
+        job.tex[k] = tex[k];
+        if (tex[k] && tex_dims) { job.tex_w[k] = tex_dims[3 * k]; job.tex_h[k] = tex_dims[3 * k + 1]; job.tex_layers[k] = tex_dims[3 * k + 2]; }
+    }
+    job.seeds = seeds; job.samples = samples; job.precision = precision; job.rng_mode = rng_mode;
+    job.devices = devices; job.n_devices = devices ? n_devices : 0;
+    return ptc_render(&job, out_rgba, err, errlen);
+}
+
 // Test hook (not part of the drop-in surface): evaluate noise3D on the device.
 int ptc_debug_noise3d(const float* xyz, int n, int rng_mode, float* out, char* err, int errlen) {
     return guarded(err, errlen, [&] {

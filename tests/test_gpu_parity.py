@@ -44,8 +44,12 @@ def test_rng_stream_is_bit_identical_to_the_oracle():
     O.lib().oracle_noise3d_array(xyz.ctypes.data, len(xyz), ref.ctypes.data)
     dev = T.debug_noise3d(xyz, T.RNG_PARITY)
     assert np.array_equal(ref.view(np.uint32), dev.view(np.uint32))
-    fast = T.debug_noise3d(xyz, T.RNG_FAST)          # different stream, same distribution
+    # the fast stream (fp32 polynomial after the exact reduction) is reproducible too
+    O.lib().oracle_noise3d_array_mode(xyz.ctypes.data, len(xyz), 1, ref.ctypes.data)
+    fast = T.debug_noise3d(xyz, T.RNG_FAST)
+    assert np.array_equal(ref.view(np.uint32), fast.view(np.uint32))
     assert fast.min() >= 0.0 and fast.max() < 1.0 and abs(fast.mean() - 0.5) < 0.01
+    assert np.mean(fast != dev) > 0.5                # ... and it is a different stream
 
 
 # scene, W, H, spp, aperture, focal length -- every material / shape / texture branch of the kernel
@@ -76,6 +80,20 @@ def test_low_spp_pixel_parity(name, W, H, spp, ap, fl, precision):
     ref, _ = O.trace(sc, seeds, spp, precision=1)
     img = T.render_scene(sc, spp, seeds, precision=precision)
     assert not np.isnan(img).any() and np.all(img[..., 3] == 1.0)
+    frac, worst = frac_within(img, ref, TOL[precision])
+    assert frac >= 0.999, f"{frac * 100:.3f}% of pixels within {TOL[precision]:g} (worst {worst:.3e})"
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name,W,H,spp,ap,fl", [("reference", 128, 96, 1, 0.15, 1.6), ("transparency", 96, 72, 2, 0.0, 0.0),
+                                                ("gopher", 96, 72, 1, 0.0, 0.0), ("textures", 64, 48, 2, 0.0, 0.0)])
+def test_fast_rng_stream_pixel_parity(name, W, H, spp, ap, fl, precision):
+    """rng_mode FAST is a second, cheaper evaluation of the same hash that the oracle reproduces bit
+    for bit (oracle/canon_rng.h), so it gets the same per-pixel gate as the parity stream."""
+    sc = S.build_scene(name, W, H, ap, fl, tex_scale=16)
+    seeds = S.make_seeds(0xFA57 + W, W * H)
+    ref, _ = O.trace(sc, seeds, spp, precision=1, rng_mode=1)
+    img = T.render_scene(sc, spp, seeds, precision=precision, rng_mode=T.RNG_FAST)
     frac, worst = frac_within(img, ref, TOL[precision])
     assert frac >= 0.999, f"{frac * 100:.3f}% of pixels within {TOL[precision]:g} (worst {worst:.3e})"
 
