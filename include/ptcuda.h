@@ -147,6 +147,10 @@ int ptc_shard_rows(const ptc_context *ctx, int32_t *rows, int cap);
 int ptc_plan_rows(int32_t height, int32_t rows_per_tile, int32_t shard_index, int32_t shard_count,
                   int32_t *rows, int cap);
 
+/* Single-GPU contexts draw device memory from a per-device pool that is kept between calls so a
+ * render pays no cudaMalloc/cudaFree; ptc_trim returns the pooled memory to the driver. */
+void ptc_trim(void);
+
 const char *ptc_version(void);
 
 #ifdef __cplusplus

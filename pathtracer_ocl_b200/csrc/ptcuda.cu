@@ -13,8 +13,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -173,7 +175,8 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<int> rows;          // frame rows owned by this device, increasing
-    std::vector<void*> allocs;      // everything cudaMalloc'ed on this device
+    std::vector<void*> allocs;      // everything allocated on this device
+    cudaMemPool_t pool = nullptr;   // stream-ordered pool (single-GPU contexts), else plain cudaMalloc
     void* shade = nullptr; void* lens = nullptr; void* node_lo = nullptr; void* node_hi = nullptr; void* node_meta = nullptr;
     void* tri_test = nullptr; void* tri_shade = nullptr;
     void* tex[3] = {nullptr, nullptr, nullptr};
@@ -204,9 +207,38 @@ struct ptc_context {
 
 namespace {
 
+// Device memory for single-GPU contexts comes from a per-device stream-ordered pool that keeps its
+// blocks between calls (release threshold = max): a render no longer pays cudaMalloc/cudaFree --
+// the latter synchronises the device and was measured to stall for up to 1.3 s inside a process
+// that also hosts another CUDA allocator.  Multi-GPU contexts use plain cudaMalloc so the peer
+// copies of the gather need no per-pool access grants.  The pool table is the only global state;
+// it is mutex-protected and holds driver handles only.  ptc_trim() returns the memory.
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {};
+
+cudaMemPool_t pool_for(int device) {
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[device]) {
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        g_pools[device] = pool;
+    }
+    return g_pools[device];
+}
+
 void* dmalloc(DeviceState& d, size_t bytes) {
     void* p = nullptr;
-    CUDA_OK(cudaMalloc(&p, bytes ? bytes : 16));
+    if (d.pool) CUDA_OK(cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, d.pool, d.stream));
+    else CUDA_OK(cudaMalloc(&p, bytes ? bytes : 16));
     d.allocs.push_back(p);
     return p;
 }
@@ -314,7 +346,12 @@ void destroy(ptc_context* c) {
     if (!c) return;
     for (DeviceState& d : c->dev) {
         cudaSetDevice(d.device);
-        for (void* p : d.allocs) cudaFree(p);
+        if (d.pool && d.stream) {
+            for (void* p : d.allocs) cudaFreeAsync(p, d.stream);     // back to the pool, no device-wide sync
+            cudaStreamSynchronize(d.stream);
+        } else {
+            for (void* p : d.allocs) cudaFree(p);
+        }
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -373,11 +410,13 @@ ptc_context* open_impl(const ptc_job& job) {
         DeviceState& d = c.dev[size_t(i)];
         d.device = devices[size_t(i)];
         CUDA_OK(cudaSetDevice(d.device));
-        cudaDeviceProp prop;
-        CUDA_OK(cudaGetDeviceProperties(&prop, d.device));
-        if (prop.major < 10) fail("device %d (%s) is sm_%d%d; libptcuda is built for sm_100a only", d.device, prop.name, prop.major, prop.minor);
-        d.sm_count = prop.multiProcessorCount;
+        int cc_major = 0, cc_minor = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, d.device));
+        CUDA_OK(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, d.device));
+        if (cc_major < 10) fail("device %d is sm_%d%d; libptcuda is built for sm_100a only", d.device, cc_major, cc_minor);
+        CUDA_OK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
         CUDA_OK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        if (nd == 1) d.pool = pool_for(d.device);
         CUDA_OK(cudaEventCreate(&d.ev0));
         CUDA_OK(cudaEventCreate(&d.ev1));
         if (c.precision == PTC_FP64) upload_scene<double>(c, d, c.scene64, h2d);
@@ -584,6 +623,12 @@ int ptc_shard_rows(const ptc_context* ctx, int32_t* rows, int cap) {
     return n;
 }
 
+void ptc_trim(void) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (cudaMemPool_t& p : g_pools)
+        if (p) cudaMemPoolTrimTo(p, 0);
+}
+
 int ptc_plan_rows(int32_t height, int32_t rows_per_tile, int32_t shard_index, int32_t shard_count, int32_t* rows, int cap) {
     if (height < 0) return -1;
     const int rpt = rows_per_tile > 0 ? rows_per_tile : 4;
@@ -601,11 +646,20 @@ int ptc_plan_rows(int32_t height, int32_t rows_per_tile, int32_t shard_index, in
 
 int ptc_render(const ptc_job* job, double* out_rgba, char* err, int errlen) {
     ptc_context* ctx = nullptr;
+    auto t0 = Clock::now();
     int rc = ptc_open(job, &ctx, err, errlen);
     if (rc != 0) return rc;
+    auto t1 = Clock::now();
     rc = ptc_trace(ctx, err, errlen);
+    auto t2 = Clock::now();
     if (rc == 0) rc = ptc_read(ctx, out_rgba, err, errlen);
+    auto t3 = Clock::now();
+    const double kernel_ms = ctx->stats.kernel_ms;
     ptc_close(ctx);
+    if (std::getenv("PTC_DEBUG_TIMING"))
+        std::fprintf(stderr, "[ptc_render] open %.2f ms, trace %.2f ms (kernel %.2f), read %.2f ms, close %.2f ms\n",
+                     std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                     kernel_ms, std::chrono::duration<double, std::milli>(t3 - t2).count(), ms_since(t3));
     return rc;
 }
 

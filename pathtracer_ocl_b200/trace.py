@@ -51,7 +51,7 @@ class PtcStats(C.Structure):
 
 
 EXPORTS = ["ptc_device_count", "ptc_device_name", "ptc_render", "ptc_open", "ptc_trace", "ptc_read", "ptc_get_stats",
-           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_plan_rows", "ptc_version", "ptc_render_flat"]
+           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_plan_rows", "ptc_version", "ptc_render_flat", "ptc_trim"]
 
 _lib = None
 
