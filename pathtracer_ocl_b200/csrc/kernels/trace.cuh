@@ -512,27 +512,42 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     V3<R> ro = {R(0), R(0), R(0)}, rd = {R(0), R(0), R(0)};
     V3<R> mask = {R(1), R(1), R(1)}, accum = {R(0), R(0), R(0)};
 
+    // Camera rays are generated one path AHEAD and parked in registers.  Generation runs only when
+    // some lane needs a ray it does not have; at that moment every lane without a parked ray makes
+    // its next one too, so the (RNG-heavy) generation code executes with most lanes active instead
+    // of with the ~quarter of the lanes whose path happened to end on this iteration.  The RNG is a
+    // pure function of (seed, sample, bounce), so evaluation order does not change any value.
+    V3<R> nxo = cam_origin, nxd = {R(0), R(0), R(0)};
+    bool have_next = false;
+
     while (true) {
         if (fresh && n >= samples) live = false;
-        if (GROUPS) { if (!__any_sync(kFullMask, live)) break; }   // the warp leaves together
-        else if (!live) break;
-        if (fresh && live) {
-            // rayForPixel, tracer.cl:745-779
-            float jx = noise3d<RNG>(fgi, (float)n, fgi2);
-            float jy = noise3d<RNG>(fgi, fgi2, (float)n);
-            R xo = P.cam.pixel_size * (px + R(jx));
-            R yo = P.cam.pixel_size * (py + R(jy));
-            V3<R> in_view = {P.cam.half_width - xo, P.cam.half_height - yo, R(-1)};
-            V3<R> pixel = xf_point(P.cam.inv, in_view);
-            ro = cam_origin;
-            rd = normalize(pixel - ro);
-            if (P.lens != nullptr) {                                                          // aperture != 0
-                V3<R> pos = ro + rd * P.cam.focal_length;
-                R sx = ldg1(&P.lens[2 * n]), sy = ldg1(&P.lens[2 * n + 1]);                     // NaN at n == 0 when samples >= 3: kept
-                V3<R> no = {ro.x + sy * P.cam.aperture, ro.y + sx * P.cam.aperture, ro.z};   // x/y swap as upstream
-                rd = pos - no;                                                                // left unnormalised
-                ro = no;
+        if (!__any_sync(kFullMask, live)) break;                 // the warp leaves together
+        const bool starved = fresh && live && !have_next;
+        if (__any_sync(kFullMask, starved)) {
+            const unsigned gn = fresh ? n : n + (unsigned)P.slices;    // the sample this lane will start next
+            if (live && !have_next && gn < samples) {
+                // rayForPixel, tracer.cl:745-779
+                float jx = noise3d<RNG>(fgi, (float)gn, fgi2);
+                float jy = noise3d<RNG>(fgi, fgi2, (float)gn);
+                R xo = P.cam.pixel_size * (px + R(jx));
+                R yo = P.cam.pixel_size * (py + R(jy));
+                V3<R> in_view = {P.cam.half_width - xo, P.cam.half_height - yo, R(-1)};
+                V3<R> pixel = xf_point(P.cam.inv, in_view);
+                nxo = cam_origin;
+                nxd = normalize(pixel - nxo);
+                if (P.lens != nullptr) {                                                          // aperture != 0
+                    V3<R> pos = nxo + nxd * P.cam.focal_length;
+                    R sx = ldg1(&P.lens[2 * gn]), sy = ldg1(&P.lens[2 * gn + 1]);                   // NaN at sample 0 when samples >= 3: kept
+                    V3<R> no = {nxo.x + sy * P.cam.aperture, nxo.y + sx * P.cam.aperture, nxo.z}; // x/y swap as upstream
+                    nxd = pos - no;                                                               // left unnormalised
+                    nxo = no;
+                }
+                have_next = true;
             }
+        }
+        if (fresh && live) {
+            ro = nxo; rd = nxd; have_next = false;
             b = 0; effective = 0; inside = false;
             mask = {R(1), R(1), R(1)}; accum = {R(0), R(0), R(0)};
             fresh = false;
