@@ -228,9 +228,12 @@ def main():
     wall = time.perf_counter() - wall0
     clocks = sampler.finish()
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)      # kernels launched by all ranks in the timed region
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    launches = int(lt[0])
     value = total_paths * a.steps / (dev_ms_max / 1e3) / 1e6
     upload_stats = ctx.stats()
 
@@ -306,9 +309,21 @@ def main():
                 "hbm_algorithmic_bytes_per_launch": len(ctx.rows) * W * 40,
                 "hbm_gbs_achieved": len(ctx.rows) * W * 40 / (kernel_ms_avg / 1e3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs")}
+    flops_source = "oracle event counters on the cpu_baseline sample of this run"
+    if flops_per_path is None:
+        # the CPU leg is skipped (N > 1 or --no-cpu-baseline): use the figure recorded for this workload in
+        # profiles/model_flops.json by an earlier N=1 run
+        try:
+            table = json.load(open(os.path.join(ROOT, "profiles", "model_flops.json")))
+            key = f"{a.scene}_{W}x{H}_ap{a.aperture:g}"
+            flops_per_path = table.get(key)
+            flops_source = f"profiles/model_flops.json[{key}]"
+        except Exception:
+            flops_per_path = None
     if flops_per_path is not None:
         achieved = flops_per_path * (total_paths / world) / (kernel_ms_avg / 1e3) / 1e12
-        roofline.update(achieved=achieved, frac=achieved / fp32_peak, model_flops_per_path=flops_per_path)
+        roofline.update(achieved=achieved, frac=achieved / fp32_peak, model_flops_per_path=flops_per_path,
+                        model_flops_source=flops_source)
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:

@@ -45,6 +45,12 @@ namespace ptk {
 #ifndef PTK_MIN_BLOCKS_F64
 #define PTK_MIN_BLOCKS_F64 3
 #endif
+#ifndef PTK_UNROLL_SLOTS
+// Compile-time object slots (constant-bank immediates instead of indexed constant loads) for mesh-free
+// scenes.  Measured on B200: SLOWER than the run loop (9.36 vs 10.64 Gpaths/s on the reference scene --
+// 16 copies of every object test cost more in instruction fetch than the loads they save), so it is off.
+#define PTK_UNROLL_SLOTS 0
+#endif
 #ifndef PTK_BLOCK_THREADS
 #define PTK_BLOCK_THREADS 128
 #endif
@@ -408,72 +414,84 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
     }
 }
 
-// Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.
+// One analytic object against one ray (`type` is warp-uniform).
+template <typename R>
+__device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int type, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
+    if (type == 0) {                                             // plane, tracer.cl:478-483
+        R oy = ob.inv[4] * ro.x + ob.inv[5] * ro.y + ob.inv[6] * ro.z + ob.inv[7];
+        R dy = ob.inv[4] * rd.x + ob.inv[5] * rd.y + ob.inv[6] * rd.z;
+        R t = m_div(-oy, dy);
+        if (m_abs(dy) > eps) offer(h, t, j, eps);
+    } else if (type == 5) {                                      // sphere whose inverse is scale+translate only
+        V3<R> o = {ob.inv[0] * ro.x + ob.inv[3], ob.inv[5] * ro.y + ob.inv[7], ob.inv[10] * ro.z + ob.inv[11]};
+        V3<R> d = {ob.inv[0] * rd.x, ob.inv[5] * rd.y, ob.inv[10] * rd.z};    // (off-diagonal terms are exact zeros)
+        R a = dot(d, d);
+        R b = R(2) * dot(d, o);
+        R c = dot(o, o) - R(1);
+        R disc = b * b - R(4) * a * c;
+        sphere_roots(h, a, b, disc, j, eps);
+    } else if (type == 1) {                                      // sphere, tracer.cl:448-476
+        V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+        R a = dot(d, d);
+        R b = R(2) * dot(d, o);
+        R c = dot(o, o) - R(1);
+        R disc = b * b - R(4) * a * c;
+        sphere_roots(h, a, b, disc, j, eps);
+    } else if (type == 2) {                                      // cylinder side, caps off, tracer.cl:396-446
+        V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+        R a = d.x * d.x + d.z * d.z;
+        if (!(m_abs(a) < eps)) {
+            R b = R(2) * o.x * d.x + R(2) * o.z * d.z;
+            R c = o.x * o.x + o.z * o.z - R(1);
+            R disc = b * b - R(4) * a * c;
+            if (!(disc < R(0))) {
+                R sq = m_sqrt(disc), inv_den = m_rcp(R(2) * a);
+                R t0 = (-b - sq) * inv_den, t1 = (-b + sq) * inv_den;
+                R y0 = o.y + t0 * d.y, y1 = o.y + t1 * d.y;
+                if (y0 > ob.aux[0] && y0 < ob.aux[1]) offer(h, t0, j, eps);
+                if (y1 > ob.aux[0] && y1 < ob.aux[1]) offer(h, t1, j, eps);
+            }
+        }
+    } else if (type == 3) {                                      // cube, tracer.cl:378-394
+        V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+        Slab<R> s = make_slab(d, eps);
+        R tmin, tmax;
+        ray_box(o, d, s, R(-1), R(-1), R(-1), R(1), R(1), R(1), tmin, tmax);
+        if (!(tmin > tmax)) { offer(h, tmin, j, eps); offer(h, tmax, j, eps); }
+    }
+}
+
+// Object slots unrolled at compile time: slot K reads P.hot[K] at a FIXED offset of the kernel
+// parameter block, so every matrix entry is an immediate constant-bank operand of its FFMA -- no
+// load instruction, no address arithmetic, no loop counter (the slot's type test is a uniform branch).
+template <typename R, int K>
+__device__ __forceinline__ void scan_slots(const Params<R>& P, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
+    if constexpr (K < kMaxObjects) {
+        if (K < P.n_objects) {
+            test_object<R>(P.hot[K], K, P.hot[K].type, ro, rd, eps, h);
+            scan_slots<R, K + 1>(P, ro, rd, eps, h);
+        }
+    }
+}
+
+// Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.  Object order is the scene's
+// (ties go to the lower index, tracer.cl:731-739).
 template <typename R, bool GROUPS>
 __device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h) {
     const R eps = P.eps;
     h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
+    if (!GROUPS && PTK_UNROLL_SLOTS) {
+        scan_slots<R, 0>(P, ro, rd, eps, h);
+        return;
+    }
+    // scenes with meshes: one dispatch per run of consecutive same-type objects
     for (int r = 0; r < P.n_runs; ++r) {
-      const int type = P.runs[r].type, jb = P.runs[r].begin, je = P.runs[r].end;
-      if (type == 0) {
-        for (int j = jb; j < je; ++j) {                          // plane, tracer.cl:478-483
-            const DObjHot<R>& ob = P.hot[j];
-            R oy = ob.inv[4] * ro.x + ob.inv[5] * ro.y + ob.inv[6] * ro.z + ob.inv[7];
-            R dy = ob.inv[4] * rd.x + ob.inv[5] * rd.y + ob.inv[6] * rd.z;
-            R t = m_div(-oy, dy);
-            if (m_abs(dy) > eps) offer(h, t, j, eps);
+        const int type = P.runs[r].type, jb = P.runs[r].begin, je = P.runs[r].end;
+        if (GROUPS && type == 4) {
+            for (int j = jb; j < je; ++j) group_hit<R>(P, P.hot[j], j, ro, rd, live, lane, h);
+        } else {
+            for (int j = jb; j < je; ++j) test_object<R>(P.hot[j], j, type, ro, rd, eps, h);
         }
-      } else if (type == 1) {
-        for (int j = jb; j < je; ++j) {                          // sphere, tracer.cl:448-476
-            const DObjHot<R>& ob = P.hot[j];
-            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            R a = dot(d, d);
-            R b = R(2) * dot(d, o);
-            R c = dot(o, o) - R(1);
-            R disc = b * b - R(4) * a * c;
-            sphere_roots(h, a, b, disc, j, eps);
-        }
-      } else if (type == 5) {
-        for (int j = jb; j < je; ++j) {                          // sphere whose inverse is scale+translate only
-            const DObjHot<R>& ob = P.hot[j];                     // (the off-diagonal terms are exact zeros)
-            V3<R> o = {ob.inv[0] * ro.x + ob.inv[3], ob.inv[5] * ro.y + ob.inv[7], ob.inv[10] * ro.z + ob.inv[11]};
-            V3<R> d = {ob.inv[0] * rd.x, ob.inv[5] * rd.y, ob.inv[10] * rd.z};
-            R a = dot(d, d);
-            R b = R(2) * dot(d, o);
-            R c = dot(o, o) - R(1);
-            R disc = b * b - R(4) * a * c;
-            sphere_roots(h, a, b, disc, j, eps);
-        }
-      } else if (type == 2) {
-        for (int j = jb; j < je; ++j) {                          // cylinder side, caps off, tracer.cl:396-446
-            const DObjHot<R>& ob = P.hot[j];
-            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            R a = d.x * d.x + d.z * d.z;
-            if (!(m_abs(a) < eps)) {
-                R b = R(2) * o.x * d.x + R(2) * o.z * d.z;
-                R c = o.x * o.x + o.z * o.z - R(1);
-                R disc = b * b - R(4) * a * c;
-                if (!(disc < R(0))) {
-                    R sq = m_sqrt(disc), inv_den = m_rcp(R(2) * a);
-                    R t0 = (-b - sq) * inv_den, t1 = (-b + sq) * inv_den;
-                    R y0 = o.y + t0 * d.y, y1 = o.y + t1 * d.y;
-                    if (y0 > ob.aux[0] && y0 < ob.aux[1]) offer(h, t0, j, eps);
-                    if (y1 > ob.aux[0] && y1 < ob.aux[1]) offer(h, t1, j, eps);
-                }
-            }
-        }
-      } else if (type == 3) {
-        for (int j = jb; j < je; ++j) {                          // cube, tracer.cl:378-394
-            const DObjHot<R>& ob = P.hot[j];
-            V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            Slab<R> s = make_slab(d, eps);
-            R tmin, tmax;
-            ray_box(o, d, s, R(-1), R(-1), R(-1), R(1), R(1), R(1), tmin, tmax);
-            if (!(tmin > tmax)) { offer(h, tmin, j, eps); offer(h, tmax, j, eps); }
-        }
-      } else if (GROUPS && type == 4) {
-        for (int j = jb; j < je; ++j) group_hit<R>(P, P.hot[j], j, ro, rd, live, lane, h);
-      }
     }
 }
 
