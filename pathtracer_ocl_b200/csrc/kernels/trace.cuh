@@ -154,8 +154,11 @@ template <typename R> struct Params {
     const DObjShade<R>* shade;  int n_objects;
     const V4<R>* node_lo;       // (min.xyz, -)
     const V4<R>* node_hi;       // (max.xyz, -)
-    const int4* node_meta;      // (tri_begin, tri_count, skip, -)
-    const V4<R>* tri_test;      // 3 per triangle: (p1.xyz,e1.x) (e1.yz,e2.xy) (e2.z,-,-,-)
+    const int4* node_meta;      // (chunk_begin, chunk_count, skip, triangle count)
+    const V4<R>* chunk_lo;      // per 32-slot triangle chunk: padded min.xyz
+    const V4<R>* chunk_hi;      //                               padded max.xyz
+    const int* tri_orig;        // per slot: index in the caller's triangle buffer (tie-break), INT_MAX = empty
+    const V4<R>* tri_test;      // 3 per slot: (p1.xyz,e1.x) (e1.yz,e2.xy) (e2.z,-,-,-)
     const V4<R>* tri_shade;     // 3 per triangle: (n1.xyz,col.r) (n2.xyz,col.g) (n3.xyz,col.b)
     const R* lens;              // 2 per sample: sunflower(samples, 2, n), tracer.cl:235-248 (NULL without DoF)
     DCam<R> cam;
@@ -365,7 +368,7 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
     int i = ob.node_begin;
     const int node_end = ob.node_end;
     while (__any_sync(kFullMask, walking)) {
-        bool post = false;
+        bool post = false, leaf = false;
         int tb = 0, te = 0;
         if (walking) {
             if (i >= node_end) walking = false;
@@ -374,7 +377,7 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
                 const int4 meta = __ldg(&P.node_meta[i]);
                 const bool hitbox = ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tmin, tmax);
                 if (!hitbox || tmin > h.t * R(1.0001) || tmax < -eps) i = meta.z;
-                else { i = i + 1; tb = meta.x; te = meta.x + meta.y; post = meta.y > 0; }
+                else { leaf = meta.z == i + 1; i = i + 1; tb = meta.x; te = meta.x + meta.y; post = meta.y > 0; }
             }
         }
         unsigned pending = __ballot_sync(kFullMask, post);
@@ -383,11 +386,25 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
             pending &= pending - 1;
             const V3<R> bo = shfl3(o, leader), bd = shfl3(d, leader);
             const int btb = __shfl_sync(kFullMask, tb, leader), bte = __shfl_sync(kFullMask, te, leader);
+            const R limit = __shfl_sync(kFullMask, h.t, leader) * R(1.0001);
+            const bool bleaf = __shfl_sync(kFullMask, (int)leaf, leader) != 0;
+            const Slab<R> bs = make_slab(bd, eps);
             R ct = m_huge<R>(), cu = R(0), cv = R(0);                // this lane's best candidate in the node
-            int ctri = 0x7fffffff;
-            for (int base = btb; base < bte; base += 32) {          // Moeller-Trumbore, tracer.cl:640-675
-                const int n = base + lane;
-                if (n < bte) {
+            int cslot = 0, corig = 0x7fffffff;
+            for (int cb = btb; cb < bte; cb += 32) {
+                // lane k tests the box of chunk cb+k (conservative: padded box, inclusive compare, NaN keeps)
+                bool chit = false;
+                if (bte - btb == 1 && bleaf) chit = lane == 0;      // a leaf's only chunk has the node's own box: already passed
+                else if (cb + lane < bte) {
+                    const V4<R> clo = ldg4(&P.chunk_lo[cb + lane]), chi = ldg4(&P.chunk_hi[cb + lane]);
+                    R c0, c1;
+                    ray_box(bo, bd, bs, clo.x, clo.y, clo.z, chi.x, chi.y, chi.z, c0, c1);
+                    chit = !(c0 > c1) && !(c0 > limit) && !(c1 < -eps);
+                }
+                unsigned cmask = __ballot_sync(kFullMask, chit);
+                while (cmask) {                                      // Moeller-Trumbore, tracer.cl:640-675
+                    const int n = (cb + __ffs(cmask) - 1) * 32 + lane;
+                    cmask &= cmask - 1;
                     const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
                     const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * n + 2].x)};
                     const V3<R> e1 = {q0.w, q1.x, q1.y};
@@ -400,15 +417,19 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
                     const R v = f * dot(bd, sxe1);
                     const R t = f * dot(e2, sxe1);
                     const bool ok = !(m_abs(det) < eps) && !(u < R(0) || u > R(1)) && !(v < R(0) || (u + v) > R(1));
-                    if (ok && t > eps && t < ct) { ct = t; ctri = n; cu = u; cv = v; }
+                    if (ok && t > eps) {
+                        const int orig = __ldg(&P.tri_orig[n]);
+                        if (t < ct || (t == ct && orig < corig)) { ct = t; cslot = n; corig = orig; cu = u; cv = v; }
+                    }
                 }
             }
-            const R wt = warp_min_pos(ct);                            // warp arg-min: smallest t, then lowest index
+            const R wt = warp_min_pos(ct);                            // warp arg-min: smallest t, then lowest original index
             if (wt < m_huge<R>()) {
-                const int wtri = __reduce_min_sync(kFullMask, (ct == wt) ? ctri : 0x7fffffff);
-                const int winner = __ffs(__ballot_sync(kFullMask, ctri == wtri)) - 1;
+                const int worig = __reduce_min_sync(kFullMask, (ct == wt) ? corig : 0x7fffffff);
+                const int winner = __ffs(__ballot_sync(kFullMask, ct == wt && corig == worig)) - 1;
                 const R wu = __shfl_sync(kFullMask, cu, winner), wv = __shfl_sync(kFullMask, cv, winner);
-                if (lane == leader && wt < h.t) { h.t = wt; h.obj = j; h.tri = wtri; h.u = wu; h.v = wv; }
+                const int wslot = __shfl_sync(kFullMask, cslot, winner);
+                if (lane == leader && wt < h.t) { h.t = wt; h.obj = j; h.tri = wslot; h.u = wu; h.v = wv; }
             }
         }
     }

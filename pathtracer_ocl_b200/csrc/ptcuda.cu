@@ -9,6 +9,8 @@
 // There is no CPU path in this library: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -61,7 +63,9 @@ template <typename R> struct HostScene {
     std::vector<R> lens;       // sunflower lens points, 2 per sample (empty without depth of field)
     std::vector<ptk::V4<R>> node_lo, node_hi;
     std::vector<int4> node_meta;
+    std::vector<ptk::V4<R>> chunk_lo, chunk_hi;   // bounding box per 32-slot triangle chunk
     std::vector<ptk::V4<R>> tri_test, tri_shade;
+    std::vector<int> tri_orig;                    // slot -> index in the caller's triangle buffer
     ptk::DCam<R> cam;
 };
 
@@ -77,19 +81,76 @@ void emit_subtree(const ptw_group* groups, int n_groups, const ptw_triangle* tri
     const int me = int(out.node_lo.size());
     out.node_lo.push_back({R(s.bb_min[0]), R(s.bb_min[1]), R(s.bb_min[2]), R(0)});
     out.node_hi.push_back({R(s.bb_max[0]), R(s.bb_max[1]), R(s.bb_max[2]), R(0)});
+    const int count = s.tri_count > 0 ? s.tri_count : 0;
+    if (count > 0 && (s.tri_offset < 0 || s.tri_offset + s.tri_count > n_tris)) fail("BVH node %d references triangles outside the buffer", g);
+    // The node's own triangles are regrouped into CHUNKS of 32 slots (one warp step each): sorted along a
+    // Morton curve of their centroids so a chunk is spatially compact, each chunk with its own bounding
+    // box.  The reference tests every triangle of a visited node; a ray that misses a chunk's box cannot
+    // hit any triangle inside it, so skipping the chunk changes no result.  Unused slots hold a degenerate
+    // triangle (zero edges -> |det| < EPSILON -> rejected like upstream).  `tri_orig` keeps each slot's
+    // index in the caller's triangle buffer: ties between equal t go to the lowest ORIGINAL index, the
+    // triangle the reference would have recorded first.
     int4 meta;
-    meta.x = int(out.tri_test.size() / 3);
-    meta.y = s.tri_count > 0 ? s.tri_count : 0;
-    meta.z = 0; meta.w = 0;
-    if (meta.y > 0 && (s.tri_offset < 0 || s.tri_offset + s.tri_count > n_tris)) fail("BVH node %d references triangles outside the buffer", g);
-    for (int k = 0; k < meta.y; ++k) {
-        const ptw_triangle& t = tris[s.tri_offset + k];
-        out.tri_test.push_back({R(t.p1[0]), R(t.p1[1]), R(t.p1[2]), R(t.e1[0])});
-        out.tri_test.push_back({R(t.e1[1]), R(t.e1[2]), R(t.e2[0]), R(t.e2[1])});
-        out.tri_test.push_back({R(t.e2[2]), R(0), R(0), R(0)});
-        out.tri_shade.push_back({R(t.n1[0]), R(t.n1[1]), R(t.n1[2]), R(t.color[0])});
-        out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
-        out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
+    meta.x = int(out.chunk_lo.size());
+    meta.y = 0; meta.z = 0; meta.w = count;
+    if (count > 0) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        std::vector<std::array<double, 3>> cen;
+        cen.resize(static_cast<size_t>(count));
+        for (int k = 0; k < count; ++k) {
+            const ptw_triangle& t = tris[s.tri_offset + k];
+            for (int a = 0; a < 3; ++a) {
+                cen[size_t(k)][size_t(a)] = (t.p1[a] + t.p2[a] + t.p3[a]) / 3.0;
+                lo[a] = std::min(lo[a], cen[size_t(k)][size_t(a)]); hi[a] = std::max(hi[a], cen[size_t(k)][size_t(a)]);
+            }
+        }
+        auto spread = [](uint32_t v) { uint64_t x = v & 0x1fffff; x = (x | x << 32) & 0x1f00000000ffffULL; x = (x | x << 16) & 0x1f0000ff0000ffULL;
+                                       x = (x | x << 8) & 0x100f00f00f00f00fULL; x = (x | x << 4) & 0x10c30c30c30c30c3ULL; x = (x | x << 2) & 0x1249249249249249ULL; return x; };
+        std::vector<std::pair<uint64_t, int>> order(static_cast<size_t>(count));
+        for (int k = 0; k < count; ++k) {
+            uint64_t code = 0;
+            for (int a = 0; a < 3; ++a) {
+                const double ext = hi[a] - lo[a];
+                const double f = ext > 0 ? (cen[size_t(k)][size_t(a)] - lo[a]) / ext : 0.0;
+                code |= spread(uint32_t(f * 2097151.0)) << a;
+            }
+            order[size_t(k)] = {code, k};
+        }
+        std::sort(order.begin(), order.end());
+        for (int c0 = 0; c0 < count; c0 += 32) {
+            double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
+            for (int k = 0; k < 32; ++k) {
+                if (c0 + k < count) {
+                    const int src = s.tri_offset + order[size_t(c0 + k)].second;
+                    const ptw_triangle& t = tris[src];
+                    for (int a = 0; a < 3; ++a) {
+                        blo[a] = std::min(blo[a], std::min(t.p1[a], std::min(t.p2[a], t.p3[a])));
+                        bhi[a] = std::max(bhi[a], std::max(t.p1[a], std::max(t.p2[a], t.p3[a])));
+                    }
+                    out.tri_test.push_back({R(t.p1[0]), R(t.p1[1]), R(t.p1[2]), R(t.e1[0])});
+                    out.tri_test.push_back({R(t.e1[1]), R(t.e1[2]), R(t.e2[0]), R(t.e2[1])});
+                    out.tri_test.push_back({R(t.e2[2]), R(0), R(0), R(0)});
+                    out.tri_shade.push_back({R(t.n1[0]), R(t.n1[1]), R(t.n1[2]), R(t.color[0])});
+                    out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
+                    out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
+                    out.tri_orig.push_back(src);
+                } else {
+                    for (int q = 0; q < 3; ++q) { out.tri_test.push_back({R(0), R(0), R(0), R(0)}); out.tri_shade.push_back({R(0), R(0), R(0), R(0)}); }
+                    out.tri_orig.push_back(0x7fffffff);
+                }
+            }
+            // pad the chunk box: the cull must never reject a ray that the exact triangle test would accept
+            R plo[3], phi[3];
+            for (int a = 0; a < 3; ++a) {
+                const double pad = 1e-4 * (bhi[a] - blo[a]) + 1e-6 * std::max(std::fabs(blo[a]), std::fabs(bhi[a])) + 1e-9;
+                plo[a] = R(blo[a] - pad); phi[a] = R(bhi[a] + pad);
+                if (double(plo[a]) > blo[a] - 0.5 * pad) plo[a] = std::nextafter(plo[a], R(-1e30));   // float rounding went inward
+                if (double(phi[a]) < bhi[a] + 0.5 * pad) phi[a] = std::nextafter(phi[a], R(1e30));
+            }
+            out.chunk_lo.push_back({plo[0], plo[1], plo[2], R(0)});
+            out.chunk_hi.push_back({phi[0], phi[1], phi[2], R(0)});
+            meta.y++;
+        }
     }
     out.node_meta.push_back(meta);
     if (s.children[0] > 0) emit_subtree(groups, n_groups, tris, n_tris, s.children[0], depth + 1, out);
@@ -178,7 +239,7 @@ struct DeviceState {
     std::vector<void*> allocs;      // everything allocated on this device
     cudaMemPool_t pool = nullptr;   // stream-ordered pool (single-GPU contexts), else plain cudaMalloc
     void* shade = nullptr; void* lens = nullptr; void* node_lo = nullptr; void* node_hi = nullptr; void* node_meta = nullptr;
-    void* tri_test = nullptr; void* tri_shade = nullptr;
+    void* tri_test = nullptr; void* tri_shade = nullptr; void* tri_orig = nullptr; void* chunk_lo = nullptr; void* chunk_hi = nullptr;
     void* tex[3] = {nullptr, nullptr, nullptr};
     double* seeds = nullptr;
     int* row_map = nullptr;
@@ -259,6 +320,9 @@ template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const Ho
     d.node_meta = upload(d, s.node_meta, h2d);
     d.tri_test = upload(d, s.tri_test, h2d);
     d.tri_shade = upload(d, s.tri_shade, h2d);
+    d.tri_orig = upload(d, s.tri_orig, h2d);
+    d.chunk_lo = upload(d, s.chunk_lo, h2d);
+    d.chunk_hi = upload(d, s.chunk_hi, h2d);
     (void)c;
 }
 
@@ -276,6 +340,9 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     P.node_meta = static_cast<const int4*>(d.node_meta);
     P.tri_test = static_cast<const ptk::V4<R>*>(d.tri_test);
     P.tri_shade = static_cast<const ptk::V4<R>*>(d.tri_shade);
+    P.tri_orig = static_cast<const int*>(d.tri_orig);
+    P.chunk_lo = static_cast<const ptk::V4<R>*>(d.chunk_lo);
+    P.chunk_hi = static_cast<const ptk::V4<R>*>(d.chunk_hi);
     P.cam = s.cam;
     for (int k = 0; k < 3; ++k) P.tex[k] = ptk::DTex{static_cast<const uchar4*>(d.tex[k]), c.tex_w[k], c.tex_h[k], c.tex_layers[k]};
     P.seeds = d.seeds;
