@@ -377,7 +377,19 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
                 const int4 meta = __ldg(&P.node_meta[i]);
                 const bool hitbox = ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tmin, tmax);
                 if (!hitbox || tmin > h.t * R(1.0001) || tmax < -eps) i = meta.z;
-                else { leaf = meta.z == i + 1; i = i + 1; tb = meta.x; te = meta.x + meta.y; post = meta.y > 0; }
+                else {
+                    leaf = meta.z == i + 1;              // a leaf's single chunk has the node's own box: nothing more to check
+                    i = i + 1; tb = meta.x; te = meta.x + meta.y; post = meta.y > 0;
+                    if (meta.y == 1 && !leaf) {
+                        // inner node with one chunk of straddling triangles: test that chunk's (thin) box here,
+                        // in parallel over the walking lanes, instead of starting a warp-wide drain for it
+                        const V4<R> clo = ldg4(&P.chunk_lo[tb]), chi = ldg4(&P.chunk_hi[tb]);
+                        R c0, c1;
+                        ray_box(o, d, s, clo.x, clo.y, clo.z, chi.x, chi.y, chi.z, c0, c1);
+                        post = !(c0 > c1) && !(c0 > h.t * R(1.0001)) && !(c1 < -eps);
+                        leaf = true;                     // box already checked
+                    }
+                }
             }
         }
         unsigned pending = __ballot_sync(kFullMask, post);
