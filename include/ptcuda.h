@@ -129,6 +129,18 @@ int  ptc_read(ptc_context *ctx, double *out_rgba, char *err, int errlen);
 int  ptc_get_stats(const ptc_context *ctx, ptc_stats *stats);
 void ptc_close(ptc_context *ctx);
 
+/* Progressive rendering (replaces the reference's 4-scanline batching as the way to
+ * bound one launch, ocltracer.go:212-223): render samples [sample_begin, sample_end) of every pixel and
+ * ADD them to the context's accumulator.  After ranges that together cover [0, samples) exactly once
+ * the result equals ptc_trace's; in between, ptc_read returns accumulated_sum / samples (a caller
+ * previewing n of N samples scales by N/n).  ptc_reset zeroes the accumulator. */
+int ptc_trace_range(ptc_context *ctx, int32_t sample_begin, int32_t sample_end, char *err, int errlen);
+int ptc_reset(ptc_context *ctx, char *err, int errlen);
+
+/* The frontend's tone step on the device (internal/app/tracer/pathtracer.go:42-59:
+ * no gamma, clamp(round(c*255)), alpha 255): rows*width*4 bytes, 8x less readback than ptc_read. */
+int ptc_read_rgba8(ptc_context *ctx, uint8_t *out_rgba8, char *err, int errlen);
+
 /* Replace the per-pixel seeds of an open context (width*height doubles, same layout as
  * ptc_job.seeds).  Mirrors the reference drawing fresh seeds for every batch. */
 int ptc_set_seeds(ptc_context *ctx, const double *seeds, char *err, int errlen);

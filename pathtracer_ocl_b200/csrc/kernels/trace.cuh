@@ -167,7 +167,9 @@ template <typename R> struct Params {
     const int* row_map;         // local row -> frame row
     double* out;                // rows * width * 4 (RGBA), or per-slice partial sums when slices > 1
     int rows;                   // local rows rendered by this device
-    int samples;
+    int samples;                // total samples per pixel (enters the RNG seeding and the final weight)
+    int sample_begin, sample_end;   // samples rendered by this launch: [begin, end) (0, samples for a full render)
+    int raw_sums;               // 1: write unweighted sums per slice even when slices == 1 (progressive accumulation)
     int slices;                 // sample slices per pixel (gridDim.y)
     R pi;                       // (double)3.14159265359f, tracer.cl:1
     R eps;                      // 0.0001, tracer.cl:4
@@ -555,7 +557,8 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     double col_r = 0.0, col_g = 0.0, col_b = 0.0;
 
     // per-path state
-    unsigned n = (unsigned)slice;      // sample index (tracer.cl:867)
+    unsigned n = (unsigned)(P.sample_begin + slice);   // sample index (tracer.cl:867)
+    const unsigned n_end = (unsigned)P.sample_end;      // == samples unless a caller renders a sample range
     unsigned b = 0, effective = 0;     // bounce counters (tracer.cl:873-884)
     bool inside = false;
     bool fresh = true;                 // need a new camera ray
@@ -572,12 +575,12 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     bool have_next = false;
 
     while (true) {
-        if (fresh && n >= samples) live = false;
+        if (fresh && n >= n_end) live = false;
         if (!__any_sync(kFullMask, live)) break;                 // the warp leaves together
         const bool starved = fresh && live && !have_next;
         if (__any_sync(kFullMask, starved)) {
             const unsigned gn = fresh ? n : n + (unsigned)P.slices;    // the sample this lane will start next
-            if (live && !have_next && gn < samples) {
+            if (live && !have_next && gn < n_end) {
                 // rayForPixel, tracer.cl:745-779
                 float jx = noise3d<RNG>(fgi, (float)gn, fgi2);
                 float jy = noise3d<RNG>(fgi, fgi2, (float)gn);
@@ -743,7 +746,7 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
 
     if (!has_pixel) return;
     const size_t pix = (size_t)ly * W + lx;
-    if (P.slices == 1) {
+    if (P.slices == 1 && !P.raw_sums) {
         const double wgt = 1.0 / (double)samples;                                    // tracer.cl:837, 1184-1187
         double4* o = reinterpret_cast<double4*>(P.out) + pix;
         *o = make_double4(col_r * wgt, col_g * wgt, col_b * wgt, 1.0);
@@ -754,16 +757,36 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
 }
 
 // Sums the per-slice partials in slice order (deterministic) and applies the 1/samples weight.
-__global__ void resolve_slices_kernel(const double4* __restrict__ partial, double4* __restrict__ out, int pixels, int slices, int samples) {
+// With `acc` the sums are first added to a running per-pixel accumulator (progressive rendering:
+// several sample ranges, each its own launch).
+__global__ void resolve_slices_kernel(const double4* __restrict__ partial, double4* __restrict__ acc, double4* __restrict__ out,
+                                      int pixels, int slices, int samples) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels) return;
     double r = 0.0, g = 0.0, b = 0.0;
+    if (acc) { double4 a = acc[i]; r = a.x; g = a.y; b = a.z; }
     for (int s = 0; s < slices; ++s) {
         double4 p = partial[(size_t)s * pixels + i];
         r += p.x; g += p.y; b += p.z;
     }
+    if (acc) acc[i] = make_double4(r, g, b, 0.0);
     const double wgt = 1.0 / (double)samples;
     out[i] = make_double4(r * wgt, g * wgt, b * wgt, 1.0);
+}
+
+// Frontend tone step on the device (reference internal/app/tracer/pathtracer.go:42-59: no gamma,
+// clamp(round(c*255)), alpha 255) so a caller that only wants the picture reads back 4 B/pixel instead of 32.
+__global__ void rgba8_kernel(const double4* __restrict__ in, uchar4* __restrict__ out, int pixels) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    const double4 c = in[i];
+    auto q = [](double v) -> unsigned char {
+        double r = round(v * 255.0);            // math.Round: half away from zero
+        if (!(r >= 0.0)) r = 0.0;               // negatives and NaN
+        if (r > 255.0) r = 255.0;
+        return (unsigned char)r;
+    };
+    out[i] = make_uchar4(q(c.x), q(c.y), q(c.z), 255);
 }
 
 // Test hook: evaluate the RNG on the device (parity tests compare it bit for bit with the oracle).

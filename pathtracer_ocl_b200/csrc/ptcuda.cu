@@ -244,7 +244,9 @@ struct DeviceState {
     double* seeds = nullptr;
     int* row_map = nullptr;
     double* out = nullptr;          // rows*W*4
-    double* partial = nullptr;      // slices*rows*W*4 when slices > 1
+    double* partial = nullptr;      // slices*rows*W*4 per-slice sums (slices > 1 or progressive)
+    double* acc = nullptr;          // rows*W*4 running sums of a progressive render
+    uchar4* rgba8 = nullptr;        // rows*W tone-mapped bytes (ptc_read_rgba8)
     int slices = 1;
     int sm_count = 0;
     float last_ms = 0.f;
@@ -347,7 +349,8 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     for (int k = 0; k < 3; ++k) P.tex[k] = ptk::DTex{static_cast<const uchar4*>(d.tex[k]), c.tex_w[k], c.tex_h[k], c.tex_layers[k]};
     P.seeds = d.seeds;
     P.row_map = d.row_map;
-    P.out = d.slices > 1 ? d.partial : d.out;
+    P.out = d.out;
+    P.sample_begin = 0; P.sample_end = c.samples; P.raw_sums = 0;
     P.rows = int(d.rows.size());
     P.samples = c.samples;
     P.slices = d.slices;
@@ -356,10 +359,23 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     return P;
 }
 
-template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScene<R>& s) {
+// Renders samples [begin, end) of every pixel this device owns.  accumulate == false: a full, self-contained
+// render (begin = 0, end = samples) whose weighted result lands in d.out.  accumulate == true: the sums are
+// added to the per-pixel accumulator d.acc (progressive rendering) and d.out = acc / samples.
+template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScene<R>& s, int begin, int end, bool accumulate) {
     const int rows = int(d.rows.size());
     if (rows == 0) return;
+    const size_t pixels = size_t(rows) * size_t(c.width);
+    const bool use_partial = d.slices > 1 || accumulate;
+    if (use_partial && !d.partial) d.partial = static_cast<double*>(dmalloc(d, size_t(d.slices) * pixels * 4 * sizeof(double)));
+    if (accumulate && !d.acc) {
+        d.acc = static_cast<double*>(dmalloc(d, pixels * 4 * sizeof(double)));
+        CUDA_OK(cudaMemsetAsync(d.acc, 0, pixels * 4 * sizeof(double), d.stream));
+    }
     ptk::Params<R> P = make_params<R>(c, d, s);
+    P.sample_begin = begin; P.sample_end = end;
+    P.raw_sums = accumulate ? 1 : 0;
+    P.out = use_partial ? d.partial : d.out;
     const int tiles_x = (c.width + ptk::kTileW - 1) / ptk::kTileW;
     const int tiles_y = (rows + ptk::kTileH - 1) / ptk::kTileH;
     const long long warps = (long long)tiles_x * tiles_y;
@@ -378,10 +394,10 @@ template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScen
     }
     CUDA_OK(cudaGetLastError());
     c.stats.kernel_launches++;
-    if (d.slices > 1) {
-        const int pixels = rows * c.width;
-        ptk::resolve_slices_kernel<<<(pixels + 255) / 256, 256, 0, d.stream>>>(reinterpret_cast<const double4*>(d.partial),
-                                                                            reinterpret_cast<double4*>(d.out), pixels, d.slices, c.samples);
+    if (use_partial) {
+        ptk::resolve_slices_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, d.stream>>>(
+            reinterpret_cast<const double4*>(d.partial), accumulate ? reinterpret_cast<double4*>(d.acc) : nullptr,
+            reinterpret_cast<double4*>(d.out), int(pixels), d.slices, c.samples);
         CUDA_OK(cudaGetLastError());
         c.stats.kernel_launches++;
     }
@@ -503,13 +519,16 @@ ptc_context* open_impl(const ptc_job& job) {
         d.out = static_cast<double*>(dmalloc(d, px * 4 * sizeof(double)));
         // Small frames cannot fill 148 SMs with one thread per pixel: split each pixel's samples
         // into interleaved slices until there are ~4 resident-warp sets of work.
-        const long long want = (long long)d.sm_count * 2048 * 2;
+        // Measured on B200 (tools/slices_time.py): blocks that live for the whole frame leave a long
+        // tail (a 1/8-frame shard ran 36.3 ms with 1 slice, 29.3 ms with 32), so aim for ~16x the
+        // resident thread capacity in total threads.
+        const long long want = (long long)d.sm_count * 2048 * 16;
         long long sl = px ? (want + (long long)px - 1) / (long long)px : 1;
+        if (const char* ov = std::getenv("PTC_SLICES")) sl = std::atoll(ov);    // tuning override
         if (sl > c.samples) sl = c.samples;
-        if (sl > 64) sl = 64;
+        if (sl > 32) sl = 32;
         if (sl < 1) sl = 1;
         d.slices = int(sl);
-        if (d.slices > 1) d.partial = static_cast<double*>(dmalloc(d, size_t(d.slices) * px * 4 * sizeof(double)));
     }
     if (nd > 1) {
         DeviceState& d0 = c.dev[0];
@@ -534,13 +553,13 @@ ptc_context* open_impl(const ptc_job& job) {
     return guard.release();
 }
 
-void trace_impl(ptc_context& c) {
+void trace_impl(ptc_context& c, int begin, int end, bool accumulate) {
     c.stats.kernel_launches = 0;
     for (DeviceState& d : c.dev) {
         CUDA_OK(cudaSetDevice(d.device));
         CUDA_OK(cudaEventRecord(d.ev0, d.stream));
-        if (c.precision == PTC_FP64) launch<double>(c, d, c.scene64);
-        else launch<float>(c, d, c.scene32);
+        if (c.precision == PTC_FP64) launch<double>(c, d, c.scene64, begin, end, accumulate);
+        else launch<float>(c, d, c.scene32, begin, end, accumulate);
         CUDA_OK(cudaEventRecord(d.ev1, d.stream));
     }
     double worst = 0.0;
@@ -643,7 +662,64 @@ int ptc_open(const ptc_job* job, ptc_context** ctx, char* err, int errlen) {
 int ptc_trace(ptc_context* ctx, char* err, int errlen) {
     return guarded(err, errlen, [&] {
         if (!ctx) fail("ptc_trace: NULL context");
-        trace_impl(*ctx);
+        trace_impl(*ctx, 0, ctx->samples, false);
+    });
+}
+
+int ptc_trace_range(ptc_context* ctx, int32_t sample_begin, int32_t sample_end, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx) fail("ptc_trace_range: NULL context");
+        if (sample_begin < 0 || sample_end > ctx->samples || sample_begin >= sample_end)
+            fail("ptc_trace_range: [%d, %d) is not a sub-range of [0, %d)", sample_begin, sample_end, ctx->samples);
+        trace_impl(*ctx, sample_begin, sample_end, true);
+    });
+}
+
+int ptc_reset(ptc_context* ctx, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx) fail("ptc_reset: NULL context");
+        for (DeviceState& d : ctx->dev) {
+            if (!d.acc) continue;
+            CUDA_OK(cudaSetDevice(d.device));
+            CUDA_OK(cudaMemsetAsync(d.acc, 0, d.rows.size() * size_t(ctx->width) * 4 * sizeof(double), d.stream));
+            CUDA_OK(cudaStreamSynchronize(d.stream));
+        }
+    });
+}
+
+int ptc_read_rgba8(ptc_context* ctx, uint8_t* out_rgba8, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx || !out_rgba8) fail("ptc_read_rgba8: NULL argument");
+        ptc_context& c = *ctx;
+        auto t0 = Clock::now();
+        const int nd = int(c.dev.size());
+        const size_t row_bytes = size_t(c.width) * 4;
+        const size_t tile_bytes = row_bytes * size_t(c.rows_per_tile);
+        c.stats.d2h_bytes = 0; c.stats.p2p_bytes = 0;
+        for (int i = 0; i < nd; ++i) {
+            DeviceState& d = c.dev[size_t(i)];
+            if (d.rows.empty()) continue;
+            CUDA_OK(cudaSetDevice(d.device));
+            const size_t pixels = d.rows.size() * size_t(c.width);
+            if (!d.rgba8) d.rgba8 = static_cast<uchar4*>(dmalloc(d, pixels * 4));
+            ptk::rgba8_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, d.stream>>>(reinterpret_cast<const double4*>(d.out), d.rgba8, int(pixels));
+            CUDA_OK(cudaGetLastError());
+            c.stats.kernel_launches++;
+            if (nd == 1) {
+                CUDA_OK(cudaMemcpyAsync(out_rgba8, d.rgba8, pixels * 4, cudaMemcpyDeviceToHost, d.stream));
+            } else {   // device i owns local tiles i, i+nd, ...: strided copy straight into the packed host frame
+                const size_t full_tiles = d.rows.size() / size_t(c.rows_per_tile), tail_rows = d.rows.size() % size_t(c.rows_per_tile);
+                if (full_tiles)
+                    CUDA_OK(cudaMemcpy2DAsync(out_rgba8 + size_t(i) * tile_bytes, size_t(nd) * tile_bytes, d.rgba8, tile_bytes, tile_bytes, full_tiles,
+                                              cudaMemcpyDeviceToHost, d.stream));
+                if (tail_rows)
+                    CUDA_OK(cudaMemcpyAsync(out_rgba8 + (full_tiles * size_t(nd) + size_t(i)) * tile_bytes, reinterpret_cast<uint8_t*>(d.rgba8) + full_tiles * tile_bytes,
+                                            tail_rows * row_bytes, cudaMemcpyDeviceToHost, d.stream));
+            }
+            c.stats.d2h_bytes += int64_t(pixels * 4);
+        }
+        for (DeviceState& d : c.dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
+        c.stats.read_ms = ms_since(t0);
     });
 }
 

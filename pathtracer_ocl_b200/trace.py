@@ -51,7 +51,8 @@ class PtcStats(C.Structure):
 
 
 EXPORTS = ["ptc_device_count", "ptc_device_name", "ptc_render", "ptc_open", "ptc_trace", "ptc_read", "ptc_get_stats",
-           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_plan_rows", "ptc_version", "ptc_render_flat", "ptc_trim"]
+           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_plan_rows", "ptc_version", "ptc_render_flat", "ptc_trim",
+           "ptc_trace_range", "ptc_reset", "ptc_read_rgba8"]
 
 _lib = None
 
@@ -78,6 +79,9 @@ def lib() -> C.CDLL:
         L.ptc_shard_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int]
         L.ptc_debug_noise3d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
         L.ptc_plan_rows.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int]
+        L.ptc_trace_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int]
+        L.ptc_reset.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_read_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -214,6 +218,25 @@ class Context:
         err = C.create_string_buffer(512)
         if lib().ptc_set_seeds(self._h, s.ctypes.data, err, 512) != 0:
             raise PtcError(err.value.decode())
+
+    def trace_range(self, sample_begin: int, sample_end: int) -> None:
+        """Progressive rendering: add samples [begin, end) of every pixel to the accumulator."""
+        err = C.create_string_buffer(512)
+        if lib().ptc_trace_range(self._h, sample_begin, sample_end, err, 512) != 0:
+            raise PtcError(err.value.decode())
+
+    def reset(self) -> None:
+        err = C.create_string_buffer(512)
+        if lib().ptc_reset(self._h, err, 512) != 0:
+            raise PtcError(err.value.decode())
+
+    def read_rgba8(self) -> np.ndarray:
+        """The frame as 8-bit RGBA (clamp(round(c*255)), alpha 255), tone-mapped on the device."""
+        out = np.empty((len(self.rows), self.width, 4), dtype=np.uint8)
+        err = C.create_string_buffer(512)
+        if lib().ptc_read_rgba8(self._h, out.ctypes.data, err, 512) != 0:
+            raise PtcError(err.value.decode())
+        return out
 
     def set_seeds_ptr(self, ptr: int) -> None:
         err = C.create_string_buffer(512)

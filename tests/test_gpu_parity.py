@@ -194,6 +194,45 @@ def test_phase_api_set_seeds_and_stats():
     assert st["d2h_bytes"] == 64 * 48 * 32 and st["h2d_bytes"] > 64 * 48 * 8
 
 
+def test_progressive_sample_ranges_equal_one_full_pass():
+    """ptc_trace_range (SURVEY 8f-3): ranges covering [0, samples) once, in any order, reproduce ptc_trace;
+    a partial accumulation is the oracle's image of those samples scaled by done/samples."""
+    W, H, spp = 64, 48, 24
+    sc = S.build_scene("transparency", W, H)
+    seeds = S.make_seeds(31, W * H)
+    full = T.render_scene(sc, spp, seeds, precision=T.FP64)
+    with T.open_scene(sc, spp, seeds, precision=T.FP64) as ctx:
+        for a, b in ((16, 24), (0, 5), (5, 16)):
+            ctx.trace_range(a, b)
+        prog = ctx.read().reshape(H, W, 4).copy()
+        ctx.reset()
+        ctx.trace_range(0, 6)
+        part = ctx.read().reshape(H, W, 4).copy()
+        with pytest.raises(T.PtcError, match="sub-range"):
+            ctx.trace_range(10, 30)
+    assert np.abs(prog - full)[..., :3].max() <= 1e-12            # same samples, different summation order
+    ref, _ = O.trace(sc, seeds, spp, precision=1)
+    assert np.abs(full - ref)[..., :3].max() <= 1e-6
+    assert part[..., :3].sum() < 0.5 * full[..., :3].sum() and part[..., :3].sum() > 0   # 6 of 24 samples, weighted by 1/24
+
+
+def test_rgba8_readback_matches_the_frontend_tone_step():
+    """ptc_read_rgba8 == clamp(round(c*255)) of the float frame (pathtracer.go:42-59)."""
+    W, H = 96, 50
+    sc = S.build_scene("default", W, H)
+    seeds = S.make_seeds(33, W * H)
+    for shard in ((0, 1), (1, 3)):
+        with T.open_scene(sc, 3, seeds, precision=T.FP32, shard_index=shard[0], shard_count=shard[1]) as ctx:
+            ctx.trace()
+            f = ctx.read().reshape(len(ctx.rows), W, 4)
+            b = ctx.read_rgba8()
+            st = ctx.stats()
+        want = np.clip(np.floor(np.abs(f[..., :3]) * 255.0 + 0.5) * np.sign(f[..., :3]), 0, 255).astype(np.uint8)
+        assert np.array_equal(b[..., :3], want) and np.all(b[..., 3] == 255)
+        assert st["d2h_bytes"] == len(f) * W * 4
+        assert b[..., :3].max() == 255 and b[..., :3].min() == 0
+
+
 def test_sample_slices_match_single_slice_sum():
     # 16x12 pixels at 256 spp is split into sample slices on the device; the result must equal the oracle's
     sc = S.build_scene("default", 16, 12)
