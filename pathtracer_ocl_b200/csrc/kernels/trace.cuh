@@ -366,7 +366,13 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
     const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
     const Slab<R> s = make_slab(d, eps);
     R tmin, tmax;
-    bool walking = live && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], tmin, tmax);
+    // ob.pad == 0: aux is the object's own AABB, tested with the reference's rule (tracer.cl:609).
+    // ob.pad == 1: the object's AABB is unbounded (always passes upstream -- the gopher's root, whose empty
+    // "DefaultGroup" widens it to +-inf); aux then holds the padded union of the root children's boxes and is a
+    // conservative pre-cull: a ray that misses it misses every root child, so nothing is lost.
+    const bool boxhit = ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], tmin, tmax);
+    bool walking = live && ((ob.pad & 1) ? !(tmin > tmax) && !(tmax < -eps) && !(tmin > h.t * R(1.0001)) : boxhit);
+    const bool cull = !(ob.pad & 2);         // node boxes verified (on the host) to contain their subtrees
     int i = ob.node_begin;
     const int node_end = ob.node_end;
     while (__any_sync(kFullMask, walking)) {
@@ -378,7 +384,7 @@ __device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& 
                 const V4<R> lo = ldg4(&P.node_lo[i]), hi = ldg4(&P.node_hi[i]);
                 const int4 meta = __ldg(&P.node_meta[i]);
                 const bool hitbox = ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tmin, tmax);
-                if (!hitbox || tmin > h.t * R(1.0001) || tmax < -eps) i = meta.z;
+                if (!hitbox || (cull && (tmin > h.t * R(1.0001) || tmax < -eps))) i = meta.z;
                 else {
                     leaf = meta.z == i + 1;              // a leaf's single chunk has the node's own box: nothing more to check
                     i = i + 1; tb = meta.x; te = meta.x + meta.y; post = meta.y > 0;

@@ -73,8 +73,19 @@ template <typename R> struct HostScene {
 // subtree of children[0], then the subtree of children[1] -- the visiting order of the reference's
 // stack walk (tracer.cl:624-714; "children[k] > 0" means "has child", scene.go:139-152).  Each
 // node's triangles are appended contiguously as it is emitted, and `skip` points past its subtree.
+// True extent of the triangles below a node, and whether every node box on the way contained it.  The
+// distance / behind-the-ray culls of the device walk rely on "a node's box contains its subtree", which
+// the reference's Divide()+Bounds() guarantee; a caller-supplied BVH that violates it is still rendered
+// correctly, just without those culls (DObjHot.pad bit 1).
+struct SubtreeInfo {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    bool consistent = true;
+    void add(const double* p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void merge(const SubtreeInfo& o) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], o.lo[a]); hi[a] = std::max(hi[a], o.hi[a]); } consistent = consistent && o.consistent; }
+};
+
 template <typename R>
-void emit_subtree(const ptw_group* groups, int n_groups, const ptw_triangle* tris, int n_tris, int g, int depth, HostScene<R>& out) {
+void emit_subtree(const ptw_group* groups, int n_groups, const ptw_triangle* tris, int n_tris, int g, int depth, HostScene<R>& out, SubtreeInfo& info) {
     if (g < 0 || g >= n_groups) fail("BVH node index %d out of range (%d groups)", g, n_groups);
     if (depth > PTW_BVH_STACK) fail("BVH deeper than %d levels (the reference's traversal stack, tracer.cl:624)", PTW_BVH_STACK);
     const ptw_group& s = groups[g];
@@ -134,6 +145,7 @@ void emit_subtree(const ptw_group* groups, int n_groups, const ptw_triangle* tri
                     out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
                     out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
                     out.tri_orig.push_back(src);
+                    info.add(t.p1); info.add(t.p2); info.add(t.p3);
                 } else {
                     for (int q = 0; q < 3; ++q) { out.tri_test.push_back({R(0), R(0), R(0), R(0)}); out.tri_shade.push_back({R(0), R(0), R(0), R(0)}); }
                     out.tri_orig.push_back(0x7fffffff);
@@ -153,9 +165,18 @@ void emit_subtree(const ptw_group* groups, int n_groups, const ptw_triangle* tri
         }
     }
     out.node_meta.push_back(meta);
-    if (s.children[0] > 0) emit_subtree(groups, n_groups, tris, n_tris, s.children[0], depth + 1, out);
-    if (s.children[1] > 0) emit_subtree(groups, n_groups, tris, n_tris, s.children[1], depth + 1, out);
+    for (int k = 0; k < 2; ++k) {
+        if (s.children[k] <= 0) continue;
+        SubtreeInfo child;
+        emit_subtree(groups, n_groups, tris, n_tris, s.children[k], depth + 1, out, child);
+        info.merge(child);
+    }
     out.node_meta[size_t(me)].z = int(out.node_lo.size());
+    for (int a = 0; a < 3; ++a) {
+        if (info.lo[a] > info.hi[a]) continue;                       // no triangles below this node
+        const double tol = 1e-9 * (1.0 + std::fabs(info.lo[a]) + std::fabs(info.hi[a]));
+        if (!(s.bb_min[a] <= info.lo[a] + tol && s.bb_max[a] >= info.hi[a] - tol)) info.consistent = false;
+    }
 }
 
 template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
@@ -195,8 +216,25 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
             if (s.child_count > 0) {
                 if (s.child_count > PTW_MAX_ROOT_CHILDREN) fail("object %d: child_count %d > %d", i, s.child_count, PTW_MAX_ROOT_CHILDREN);
                 if (!groups || job.n_groups <= 0) fail("object %d is a group but no BVH groups were passed", i);
-                for (int c = 0; c < s.child_count; ++c) emit_subtree<R>(groups, job.n_groups, tris, job.n_triangles, s.children[c], 0, out);
+                SubtreeInfo all;
+                for (int c = 0; c < s.child_count; ++c) {
+                    SubtreeInfo child;
+                    emit_subtree<R>(groups, job.n_groups, tris, job.n_triangles, s.children[c], 0, out, child);
+                    all.merge(child);
+                }
                 h.node_end = int(out.node_lo.size());
+                if (!all.consistent) h.pad |= 2;                    // some node box does not contain its subtree: no culling
+                const bool unbounded = std::isinf(s.bb_min[0]) && std::isinf(s.bb_min[1]) && std::isinf(s.bb_min[2]) && s.bb_min[0] < 0 &&
+                                       std::isinf(s.bb_max[0]) && std::isinf(s.bb_max[1]) && std::isinf(s.bb_max[2]) && s.bb_max[0] > 0;
+                if (unbounded && all.consistent && all.lo[0] <= all.hi[0]) {
+                    // An all-infinite object box always passes upstream; replace it by the padded extent of the
+                    // triangles as a conservative pre-cull (pad bit 0) so rays far from the mesh skip the root walk.
+                    for (int a = 0; a < 3; ++a) {
+                        const double padv = 1e-4 * (all.hi[a] - all.lo[a]) + 1e-6 * std::max(std::fabs(all.lo[a]), std::fabs(all.hi[a])) + 1e-9;
+                        h.aux[a] = R(all.lo[a] - 2 * padv); h.aux[3 + a] = R(all.hi[a] + 2 * padv);
+                    }
+                    h.pad |= 1;
+                }
             }
         }
         out.shade.push_back(o);

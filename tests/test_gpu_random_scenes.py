@@ -102,6 +102,30 @@ def test_random_scene_pixel_parity(seed):
         assert frac >= 0.999, f"seed {seed} precision {precision}: {frac * 100:.3f}% within {tol:g} (worst {err.max():.3e})"
 
 
+def test_bvh_whose_boxes_do_not_contain_their_triangles():
+    """The device walk culls by distance only when the host verified that node boxes contain their
+    subtrees.  A caller-supplied BVH that violates this must still give the reference's answer: a
+    triangle is tested iff the boxes on its node chain are hit, whatever those boxes are."""
+    W, H = 96, 72
+    sc = S.build_scene("teapot", W, H)
+    groups = sc.groups.copy()
+    g = groups.view(S.GROUP_DTYPE)
+    rng = np.random.default_rng(5)
+    for k in rng.choice(len(g), 40, replace=False):          # shrink 40 node boxes towards their centre
+        c = 0.5 * (g["bb_min"][k][:3] + g["bb_max"][k][:3])
+        g["bb_min"][k][:3] = c + 0.6 * (g["bb_min"][k][:3] - c)
+        g["bb_max"][k][:3] = c + 0.6 * (g["bb_max"][k][:3] - c)
+    bad = S.SceneBuffers("teapot-shrunk", W, H, sc.objects, sc.triangles, groups, sc.camera)
+    seeds = S.make_seeds(77, W * H)
+    ref, _ = O.trace(bad, seeds, 1, precision=1)
+    good, _ = O.trace(sc, seeds, 1, precision=1)
+    assert np.abs(ref - good).max() > 0.1                    # the damage is visible in the oracle's image
+    for precision, tol in ((T.FP64, 1e-6), (T.FP32, 1e-3)):
+        img = T.render_scene(bad, 1, seeds, precision=precision)
+        err = np.abs(img[..., :3] - ref[..., :3]).max(axis=-1)
+        assert float((err <= tol).mean()) >= 0.999, float((err <= tol).mean())
+
+
 def test_random_scene_with_mesh_and_fast_rng():
     """A mesh object among random primitives, fast RNG stream, both precisions."""
     W, H, spp = 96, 72, 2
