@@ -170,6 +170,25 @@ def test_read_imagef_linear_repeat():
     assert _sample(tex, 0.3, 0.3, 0.4)[1] == 0.0
 
 
+def test_unorm8_multiply_refine_equals_division():
+    """The kernel converts texels with q = c*r; q += fma(-q,255,c)*r (r = float(1/255)) instead of an IEEE
+    divide; this replays that sequence for all 256 inputs (FMAs emulated exactly in float64) against c/255."""
+    c = np.arange(256, dtype=np.float32)
+    want = (c / np.float32(255.0)).astype(np.float32)
+    r = np.float32(float.fromhex("0x1.010102p-8"))
+    assert r == np.float32(1.0) / np.float32(255.0)
+    q = (c * r).astype(np.float32)
+    e = (c.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)
+    q2 = (q.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
+    assert np.array_equal(q2, want)
+    assert int((q != want).sum()) > 100          # the plain multiply alone would NOT do
+    # and the oracle's texel() is that same c/255.0f
+    tex = np.zeros((1, 1, 256, 4), np.uint8)
+    tex[0, 0, :, 0] = np.arange(256)
+    for k in (0, 1, 77, 128, 254, 255):
+        assert _sample(tex, (k + 0.5) / 256.0, 0.5)[0] == want[k]
+
+
 def test_schlick_total_internal_reflection():          # tracer.cl:485-505
     eye = _t([0, math.sqrt(2) / 2, math.sqrt(2) / 2, 0])   # 45 degrees inside glass
     n = _t([0, 1, 0, 0])
