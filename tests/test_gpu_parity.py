@@ -259,6 +259,24 @@ def test_process_shards_tile_the_frame(world, rpt):
     assert seen.all()
 
 
+def test_shard_without_rows_is_a_no_op():
+    """More shards than scanline tiles: the surplus shards own nothing and every call still succeeds."""
+    W, H = 32, 8                      # two 4-row tiles
+    sc = S.build_scene("default", W, H)
+    seeds = S.make_seeds(3, W * H)
+    full = T.render_scene(sc, 1, seeds)
+    got = np.zeros_like(full)
+    for r in range(5):
+        with T.open_scene(sc, 1, seeds, shard_index=r, shard_count=5) as ctx:
+            ctx.trace()
+            part = ctx.read()
+            assert part.size == len(ctx.rows) * W * 4 and len(ctx.rows) == (4 if r < 2 else 0)
+            if len(ctx.rows):
+                got[ctx.rows] = part.reshape(len(ctx.rows), W, 4)
+                assert ctx.read_rgba8().shape == (len(ctx.rows), W, 4)
+    assert np.array_equal(got, full)
+
+
 def test_one_process_driving_several_gpus_matches_single_gpu():
     """ptc_job.devices with >1 entries: interleaved tiles per device, gathered by strided peer copies.
     Needs a box with >= 2 GPUs (gpurun --gpus 2); the single-GPU result is the reference."""
