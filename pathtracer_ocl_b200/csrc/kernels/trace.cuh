@@ -148,18 +148,33 @@ template <typename R> struct DCam {
 
 struct DTex { const uchar4* data; int w, h, layers; };
 
+// Per mesh (group) object: what the rebuilt BVH needs besides the object's hot record.
+template <typename R> struct alignas(16) DMesh {
+    R root_lo[3], root_hi[3];   // padded extent of the object's triangles: conservative pre-cull
+    int bvh_root;               // index of the object's root node in bvh_*; -1 = no triangles
+    int flags;                  // bit0: every reference node box contains its child boxes (checked on the host in R)
+};
+
+constexpr int kMeshStack = 40;  // deferred-child stack entries per walking thread (host refuses deeper trees)
+
 template <typename R> struct Params {
     DObjHot<R> hot[kMaxObjects];
     DRun runs[kMaxObjects];     int n_runs;
     const DObjShade<R>* shade;  int n_objects;
+    // reference BVH (the caller's groups) re-emitted in the reference's visiting order: only the boxes and the
+    // parent links are kept, for the "would the reference have tested this triangle" check
     const V4<R>* node_lo;       // (min.xyz, -)
     const V4<R>* node_hi;       // (max.xyz, -)
-    const int4* node_meta;      // (chunk_begin, chunk_count, skip, triangle count)
-    const V4<R>* chunk_lo;      // per 32-slot triangle chunk: padded min.xyz
-    const V4<R>* chunk_hi;      //                               padded max.xyz
-    const int* tri_orig;        // per slot: index in the caller's triangle buffer (tie-break), INT_MAX = empty
+    const int* node_parent;     // -1 for a root child
+    // rebuilt BVH: binary, SAH, triangles in leaves only; a node holds the padded boxes of its two children
+    const V4<R>* bvh_a;         // (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
+    const V4<R>* bvh_b;         // (c0.lo.z, c0.hi.z, c1.lo.x, c1.hi.x)
+    const V4<R>* bvh_c;         // (c1.lo.y, c1.hi.y, c1.lo.z, c1.hi.z)
+    const int2* bvh_child;      // >= 0: inner node; < 0: leaf, ~code = (first slot << 3) | triangle count
+    const DMesh<R>* mesh;       // per object (valid for groups)
+    const int2* tri_info;       // per slot: (rank in the reference's recording order, reference node)
     const V4<R>* tri_test;      // 3 per slot: (p1.xyz,e1.x) (e1.yz,e2.xy) (e2.z,-,-,-)
-    const V4<R>* tri_shade;     // 3 per triangle: (n1.xyz,col.r) (n2.xyz,col.g) (n3.xyz,col.b)
+    const V4<R>* tri_shade;     // 3 per slot: (n1.xyz,col.r) (n2.xyz,col.g) (n3.xyz,col.b)
     const R* lens;              // 2 per sample: sunflower(samples, 2, n), tracer.cl:235-248 (NULL without DoF)
     DCam<R> cam;
     DTex tex[3];
@@ -171,6 +186,7 @@ template <typename R> struct Params {
     int sample_begin, sample_end;   // samples rendered by this launch: [begin, end) (0, samples for a full render)
     int raw_sums;               // 1: write unweighted sums per slice even when slices == 1 (progressive accumulation)
     int slices;                 // sample slices per pixel (gridDim.y)
+    int drain_threshold;        // mesh kernel: queued rays that trigger a block-wide BVH pass
     R pi;                       // (double)3.14159265359f, tracer.cl:1
     R eps;                      // 0.0001, tracer.cl:4
 };
@@ -345,124 +361,148 @@ template <typename R> __device__ __forceinline__ void sphere_roots(Hit<R>& h, V3
     offer(h, (-hb + sq) * inv_a, j, eps);
 }
 
-// ---- warp-cooperative BVH walk -------------------------------------------------------------------
+// ---- mesh objects: rebuilt BVH, reference semantics ------------------------------------------------
 constexpr unsigned kFullMask = 0xffffffffu;
 
-template <typename R> __device__ __forceinline__ V3<R> shfl3(V3<R> v, int src) {
-    return {__shfl_sync(kFullMask, v.x, src), __shfl_sync(kFullMask, v.y, src), __shfl_sync(kFullMask, v.z, src)};
-}
-// Smallest t over the warp (t > 0 or +inf): one REDUX on the bit pattern for fp32, a shuffle tree for fp64.
-__device__ __forceinline__ float warp_min_pos(float t) { return __uint_as_float(__reduce_min_sync(kFullMask, __float_as_uint(t))); }
-__device__ __forceinline__ double warp_min_pos(double t) {
-#pragma unroll
-    for (int k = 16; k > 0; k >>= 1) t = fmin(t, __shfl_xor_sync(kFullMask, t, k));
-    return t;
+// What the reference does for a group object (tracer.cl:598-720): object AABB, then for every root
+// child an in-order walk of the caller's BVH in which EVERY triangle of EVERY node whose box chain the
+// ray "hits" (tracer.cl:270-280: tmin < tmax, no t range, |d| < EPSILON -> +-HUGE_VAL) is tested and
+// recorded; the winner is the smallest recorded t in (EPSILON, 1024), earliest recorded on ties.  The Go
+// frontend's BVH keeps straddling triangles in inner nodes (46 % of the teapot's), so that walk tests
+// hundreds of triangles per ray.
+//
+// Here the triangles of a group object are re-indexed by a binary SAH BVH with leaves of <= 4 triangles,
+// built by the host layer over the SAME triangle records.  Two facts make the result the reference's:
+//   (1) the rebuilt tree only ever culls: its boxes are padded supersets of their triangles and the
+//       slab test keeps a box on any doubt (relative slack, NaN keeps), so every triangle whose
+//       Moeller-Trumbore test could pass with EPSILON < t <= best-so-far is tested, with the reference's
+//       arithmetic;
+//   (2) a triangle that passes is accepted only if the reference would have tested it, i.e. if the ray
+//       hits (reference rule, reference boxes) every node from the triangle's own reference node up to
+//       its root child.  When parent boxes contain child boxes (checked on the host in the kernel's
+//       arithmetic type) and no direction component is below EPSILON, the per-axis intervals of an
+//       ancestor contain those of the node exactly -- every operation of the slab test is monotonic
+//       under rounding -- so testing the triangle's own node box decides the whole chain; otherwise the
+//       chain is walked through the parent links.
+// Ties between equal t go to the lower rank (= position in the reference's recording order).
+template <typename R> struct IDir { R x, y, z; };
+__device__ __forceinline__ IDir<float> inv_dir(V3<float> d) { return {m_rcp(d.x), m_rcp(d.y), m_rcp(d.z)}; }
+__device__ __forceinline__ IDir<double> inv_dir(V3<double> d) { return {1.0 / d.x, 1.0 / d.y, 1.0 / d.z}; }
+template <typename R> __device__ __forceinline__ R box_slack();
+template <> __device__ __forceinline__ float box_slack<float>() { return 8e-6f; }
+template <> __device__ __forceinline__ double box_slack<double>() { return 1e-13; }
+
+// Conservative slab interval of a padded box: [tn, tf] clipped to [0, limit]; "keep" unless provably empty.
+// fmin/fmax drop a NaN operand (0 * inf on an axis the ray is parallel to), which only widens the interval.
+template <typename R>
+__device__ __forceinline__ bool keep_box(V3<R> o, IDir<R> k, R lx, R hx, R ly, R hy, R lz, R hz, R limit, R& tn) {
+    const R x0 = (lx - o.x) * k.x, x1 = (hx - o.x) * k.x;
+    const R y0 = (ly - o.y) * k.y, y1 = (hy - o.y) * k.y;
+    const R z0 = (lz - o.z) * k.z, z1 = (hz - o.z) * k.z;
+    tn = m_max(m_max(m_min(x0, x1), m_min(y0, y1)), m_max(m_min(z0, z1), R(0)));
+    const R tf = m_min(m_min(m_max(x0, x1), m_max(y0, y1)), m_min(m_max(z0, z1), limit));
+    return !(tn > tf + tf * box_slack<R>());
 }
 
-// One group object (tracer.cl:598-720): object AABB, then the BVH below its root children.
-//
-// The reference walks the tree per work-item and tests every triangle of every node whose box the
-// ray hits; inner nodes of the Go-built BVH hold up to hundreds of triangles, so per-lane triangle
-// loops diverge badly (one lane inside the mesh stalls 31 others).  Here the work is split by kind:
-//   * each lane walks the node list for its OWN ray -- box tests only, one node per step, in the
-//     reference's visiting order (the pre-order list with skip links needs no stack);
-//   * when a lane reaches a node that holds triangles it posts it, and the warp drains the posted
-//     nodes one at a time: the ray is broadcast and the 32 lanes test 32 consecutive triangles at
-//     once, then a warp arg-min (smallest t > EPSILON, ties to the lowest triangle index = the one
-//     the reference would have recorded first) hands the result back to the owning lane.
-// Nodes whose box lies entirely beyond the lane's closest hit so far, or entirely behind the ray,
-// cannot contain the winner (a triangle's hit point lies inside its node's box) and are skipped
-// with their subtree -- a pure cull, the result is the reference's.
+// (2) above.  `g` is the triangle's reference node.
 template <typename R>
-__device__ __forceinline__ void group_hit(const Params<R>& P, const DObjHot<R>& ob, int j, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h) {
-    const R eps = P.eps;
-    const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-    const Slab<R> s = make_slab(d, eps);
-    R tmin, tmax;
-    // ob.pad == 0: aux is the object's own AABB, tested with the reference's rule (tracer.cl:609).
-    // ob.pad == 1: the object's AABB is unbounded (always passes upstream -- the gopher's root, whose empty
-    // "DefaultGroup" widens it to +-inf); aux then holds the padded union of the root children's boxes and is a
-    // conservative pre-cull: a ray that misses it misses every root child, so nothing is lost.
-    const bool boxhit = ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], tmin, tmax);
-    bool walking = live && ((ob.pad & 1) ? !(tmin > tmax) && !(tmax < -eps) && !(tmin > h.t * R(1.0001)) : boxhit);
-    const bool cull = !(ob.pad & 2);         // node boxes verified (on the host) to contain their subtrees
-    int i = ob.node_begin;
-    const int node_end = ob.node_end;
-    while (__any_sync(kFullMask, walking)) {
-        bool post = false, leaf = false;
-        int tb = 0, te = 0;
-        if (walking) {
-            if (i >= node_end) walking = false;
-            else {
-                const V4<R> lo = ldg4(&P.node_lo[i]), hi = ldg4(&P.node_hi[i]);
-                const int4 meta = __ldg(&P.node_meta[i]);
-                const bool hitbox = ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tmin, tmax);
-                if (!hitbox || (cull && (tmin > h.t * R(1.0001) || tmax < -eps))) i = meta.z;
-                else {
-                    leaf = meta.z == i + 1;              // a leaf's single chunk has the node's own box: nothing more to check
-                    i = i + 1; tb = meta.x; te = meta.x + meta.y; post = meta.y > 0;
-                    if (meta.y == 1 && !leaf) {
-                        // inner node with one chunk of straddling triangles: test that chunk's (thin) box here,
-                        // in parallel over the walking lanes, instead of starting a warp-wide drain for it
-                        const V4<R> clo = ldg4(&P.chunk_lo[tb]), chi = ldg4(&P.chunk_hi[tb]);
-                        R c0, c1;
-                        ray_box(o, d, s, clo.x, clo.y, clo.z, chi.x, chi.y, chi.z, c0, c1);
-                        post = !(c0 > c1) && !(c0 > h.t * R(1.0001)) && !(c1 < -eps);
-                        leaf = true;                     // box already checked
-                    }
-                }
-            }
+__device__ __forceinline__ bool reference_tests_node(const Params<R>& P, V3<R> o, V3<R> d, const Slab<R>& s, int g, bool whole_chain) {
+    R t0, t1;
+    do {
+        const V4<R> lo = ldg4(&P.node_lo[g]), hi = ldg4(&P.node_hi[g]);
+        if (!ray_box(o, d, s, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, t0, t1)) return false;
+        g = whole_chain ? __ldg(&P.node_parent[g]) : -1;
+    } while (g >= 0);
+    return true;
+}
+
+// Does any mesh object need its BVH walked for this ray?  (object AABB under the reference rule AND the
+// padded extent of its triangles within reach of the closest hit so far)
+template <typename R>
+__device__ __forceinline__ bool mesh_wanted(const Params<R>& P, V3<R> ro, V3<R> rd, R best_t) {
+    bool want = false;
+    for (int r = 0; r < P.n_runs; ++r) {
+        if (P.runs[r].type != 4) continue;
+        for (int j = P.runs[r].begin; j < P.runs[r].end; ++j) {
+            const DObjHot<R>& ob = P.hot[j];
+            const DMesh<R>& m = P.mesh[j];
+            if (m.bvh_root < 0) continue;
+            const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+            const Slab<R> s = make_slab(d, P.eps);
+            R t0, t1, tn;
+            const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);      // NaN / inf rays hit nothing upstream
+            if (finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1) &&
+                keep_box(o, inv_dir(d), m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], best_t * R(1.0001), tn))
+                want = true;
         }
-        unsigned pending = __ballot_sync(kFullMask, post);
-        while (pending) {
-            const int leader = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const V3<R> bo = shfl3(o, leader), bd = shfl3(d, leader);
-            const int btb = __shfl_sync(kFullMask, tb, leader), bte = __shfl_sync(kFullMask, te, leader);
-            const R limit = __shfl_sync(kFullMask, h.t, leader) * R(1.0001);
-            const bool bleaf = __shfl_sync(kFullMask, (int)leaf, leader) != 0;
-            const Slab<R> bs = make_slab(bd, eps);
-            R ct = m_huge<R>(), cu = R(0), cv = R(0);                // this lane's best candidate in the node
-            int cslot = 0, corig = 0x7fffffff;
-            for (int cb = btb; cb < bte; cb += 32) {
-                // lane k tests the box of chunk cb+k (conservative: padded box, inclusive compare, NaN keeps)
-                bool chit = false;
-                if (bte - btb == 1 && bleaf) chit = lane == 0;      // a leaf's only chunk has the node's own box: already passed
-                else if (cb + lane < bte) {
-                    const V4<R> clo = ldg4(&P.chunk_lo[cb + lane]), chi = ldg4(&P.chunk_hi[cb + lane]);
-                    R c0, c1;
-                    ray_box(bo, bd, bs, clo.x, clo.y, clo.z, chi.x, chi.y, chi.z, c0, c1);
-                    chit = !(c0 > c1) && !(c0 > limit) && !(c1 < -eps);
-                }
-                unsigned cmask = __ballot_sync(kFullMask, chit);
-                while (cmask) {                                      // Moeller-Trumbore, tracer.cl:640-675
-                    const int n = (cb + __ffs(cmask) - 1) * 32 + lane;
-                    cmask &= cmask - 1;
-                    const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
-                    const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * n + 2].x)};
-                    const V3<R> e1 = {q0.w, q1.x, q1.y};
-                    const V3<R> dxe2 = cross(bd, e2);
-                    const R det = dot(e1, dxe2);
-                    const R f = m_rcp(det);
-                    const V3<R> sv = {bo.x - q0.x, bo.y - q0.y, bo.z - q0.z};
-                    const R u = f * dot(sv, dxe2);
-                    const V3<R> sxe1 = cross(sv, e1);
-                    const R v = f * dot(bd, sxe1);
-                    const R t = f * dot(e2, sxe1);
-                    const bool ok = !(m_abs(det) < eps) && !(u < R(0) || u > R(1)) && !(v < R(0) || (u + v) > R(1));
-                    if (ok && t > eps) {
-                        const int orig = __ldg(&P.tri_orig[n]);
-                        if (t < ct || (t == ct && orig < corig)) { ct = t; cslot = n; corig = orig; cu = u; cv = v; }
+    }
+    return want;
+}
+
+// All mesh objects against one ray, per lane.  In: the closest analytic hit (ct, cobj).  Out: updated
+// (ct, cobj) and, when a triangle won, its slot and barycentrics.  `stk` is this thread's column of the
+// shared-memory stack (stride = block size).
+template <typename R>
+__device__ __forceinline__ void mesh_walk(const Params<R>& P, V3<R> ro, V3<R> rd, R& ct, int& cobj, int& cslot, R& cu, R& cv,
+                                          int* __restrict__ stk, int stride) {
+    const R eps = P.eps;
+    for (int r = 0; r < P.n_runs; ++r) {
+        if (P.runs[r].type != 4) continue;
+        for (int j = P.runs[r].begin; j < P.runs[r].end; ++j) {
+            const DObjHot<R>& ob = P.hot[j];
+            const DMesh<R>& m = P.mesh[j];
+            if (m.bvh_root < 0) continue;
+            const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+            const Slab<R> s = make_slab(d, eps);
+            const IDir<R> k = inv_dir(d);
+            R t0, t1, tn0, tn1;
+            const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);
+            if (!(finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1))) continue;   // tracer.cl:609
+            if (!keep_box(o, k, m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], ct * R(1.0001), tn0)) continue;
+            // equal t: an earlier object keeps the hit (first recorded wins), a later one loses it to this mesh
+            int crank = cobj > j ? 0x7fffffff : -1;
+            const bool whole_chain = !(m.flags & 1) || !(s.dx && s.dy && s.dz);
+            int node = m.bvh_root, sp = 0;
+            while (true) {
+                if (node >= 0) {
+                    const V4<R> na = ldg4(&P.bvh_a[node]), nb = ldg4(&P.bvh_b[node]), nc = ldg4(&P.bvh_c[node]);
+                    const int2 ch = __ldg(&P.bvh_child[node]);
+                    const R limit = ct * R(1.0001);
+                    const bool h0 = keep_box(o, k, na.x, na.y, na.z, na.w, nb.x, nb.y, limit, tn0);
+                    const bool h1 = keep_box(o, k, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, limit, tn1);
+                    if (h0 && h1) {
+                        const bool swap = tn1 < tn0;                  // nearer child first
+                        stk[sp * stride] = swap ? ch.x : ch.y; ++sp;
+                        node = swap ? ch.y : ch.x;
+                        continue;
+                    }
+                    if (h0 || h1) { node = h0 ? ch.x : ch.y; continue; }
+                } else {
+                    const int code = ~node, first = code >> 3, count = code & 7;
+                    for (int q = 0; q < count; ++q) {                   // Moeller-Trumbore, tracer.cl:640-675
+                        const int n = first + q;
+                        const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
+                        const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * n + 2].x)};
+                        const V3<R> e1 = {q0.w, q1.x, q1.y};
+                        const V3<R> dxe2 = cross(d, e2);
+                        const R det = dot(e1, dxe2);
+                        const R f = m_rcp(det);
+                        const V3<R> sv = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
+                        const R u = f * dot(sv, dxe2);
+                        const V3<R> sxe1 = cross(sv, e1);
+                        const R v = f * dot(d, sxe1);
+                        const R t = f * dot(e2, sxe1);
+                        const bool ok = !(m_abs(det) < eps) && !(u < R(0) || u > R(1)) && !(v < R(0) || (u + v) > R(1));
+                        if (ok && t > eps && t <= ct) {
+                            const int2 info = __ldg(&P.tri_info[n]);
+                            if ((t < ct || info.x < crank) && reference_tests_node(P, o, d, s, info.y, whole_chain)) {
+                                ct = t; crank = info.x; cobj = j; cslot = n; cu = u; cv = v;
+                            }
+                        }
                     }
                 }
-            }
-            const R wt = warp_min_pos(ct);                            // warp arg-min: smallest t, then lowest original index
-            if (wt < m_huge<R>()) {
-                const int worig = __reduce_min_sync(kFullMask, (ct == wt) ? corig : 0x7fffffff);
-                const int winner = __ffs(__ballot_sync(kFullMask, ct == wt && corig == worig)) - 1;
-                const R wu = __shfl_sync(kFullMask, cu, winner), wv = __shfl_sync(kFullMask, cv, winner);
-                const int wslot = __shfl_sync(kFullMask, cslot, winner);
-                if (lane == leader && wt < h.t) { h.t = wt; h.obj = j; h.tri = wslot; h.u = wu; h.v = wv; }
+                if (sp == 0) break;
+                --sp; node = stk[sp * stride];
             }
         }
     }
@@ -520,62 +560,234 @@ __device__ __forceinline__ void scan_slots(const Params<R>& P, V3<R> ro, V3<R> r
     }
 }
 
-// Scene scan for one ray: tracer.cl:537-742 findClosestIntersection.  Object order is the scene's
-// (ties go to the lower index, tracer.cl:731-739).
-template <typename R, bool GROUPS>
-__device__ __forceinline__ void closest_hit(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h) {
+// Analytic objects against one ray: tracer.cl:537-597 of findClosestIntersection.  Object order is the
+// scene's (ties go to the lower index, tracer.cl:731-739).  Mesh objects are handled by mesh_walk.
+template <typename R>
+__device__ __forceinline__ void closest_analytic(const Params<R>& P, V3<R> ro, V3<R> rd, Hit<R>& h) {
     const R eps = P.eps;
     h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
-    if (!GROUPS && PTK_UNROLL_SLOTS) {
+    if (PTK_UNROLL_SLOTS) {
         scan_slots<R, 0>(P, ro, rd, eps, h);
         return;
     }
-    // scenes with meshes: one dispatch per run of consecutive same-type objects
-    for (int r = 0; r < P.n_runs; ++r) {
+    for (int r = 0; r < P.n_runs; ++r) {                 // one dispatch per run of consecutive same-type objects
         const int type = P.runs[r].type, jb = P.runs[r].begin, je = P.runs[r].end;
-        if (GROUPS && type == 4) {
-            for (int j = jb; j < je; ++j) group_hit<R>(P, P.hot[j], j, ro, rd, live, lane, h);
-        } else {
-            for (int j = jb; j < je; ++j) test_object<R>(P.hot[j], j, type, ro, rd, eps, h);
-        }
+        if (type == 4) continue;
+        for (int j = jb; j < je; ++j) test_object<R>(P.hot[j], j, type, ro, rd, eps, h);
     }
 }
 
-// GROUPS = the scene contains mesh objects: only then is the warp-cooperative walk compiled in and
-// the warp kept together until its last lane finishes.
-template <typename R, int RNG, bool GROUPS>
-__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS)) trace_kernel(const __grid_constant__ Params<R> P) {
+// Per-thread path state of the segment loop.
+template <typename R> struct Path {
+    V3<R> ro, rd;           // current ray
+    V3<R> mask, accum;      // tracer.cl:1116
+    unsigned n;             // sample index (tracer.cl:867)
+    unsigned b, effective;  // bounce counters (tracer.cl:873-884)
+    bool inside;
+};
+
+// rayForPixel, tracer.cl:745-779, for sample `gn` of pixel (px, py)
+template <typename R, int RNG>
+__device__ __forceinline__ void camera_ray(const Params<R>& P, R px, R py, float fgi, float fgi2, unsigned gn, V3<R> cam_origin, V3<R>& nxo, V3<R>& nxd) {
+    float jx = noise3d<RNG>(fgi, (float)gn, fgi2);
+    float jy = noise3d<RNG>(fgi, fgi2, (float)gn);
+    R xo = P.cam.pixel_size * (px + R(jx));
+    R yo = P.cam.pixel_size * (py + R(jy));
+    V3<R> in_view = {P.cam.half_width - xo, P.cam.half_height - yo, R(-1)};
+    V3<R> pixel = xf_point(P.cam.inv, in_view);
+    nxo = cam_origin;
+    nxd = normalize(pixel - nxo);
+    if (P.lens != nullptr) {                                                          // aperture != 0
+        V3<R> pos = nxo + nxd * P.cam.focal_length;
+        R sx = ldg1(&P.lens[2 * gn]), sy = ldg1(&P.lens[2 * gn + 1]);                   // NaN at sample 0 when samples >= 3: kept
+        V3<R> no = {nxo.x + sy * P.cam.aperture, nxo.y + sx * P.cam.aperture, nxo.z}; // x/y swap as upstream
+        nxd = pos - no;                                                               // left unnormalised
+        nxo = no;
+    }
+}
+
+// One surface interaction: normal, material branch, next ray, fused mask/accumulate (tracer.cl:895-1107,
+// 1116-1176).  Returns true when the path ends here.
+template <typename R, int RNG>
+__device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, Path<R>& s, float fgi) {
+    const R eps = P.eps, pi = P.pi;
+    V3<R>& ro = s.ro; V3<R>& rd = s.rd;
+    const unsigned n = s.n;
+    const DObjShade<R>& ob = P.shade[h.obj];
+    const int type = ob.type;
+    V3<R> position = ro + rd * h.t;
+    V3<R> eye = {-rd.x, -rd.y, -rd.z};
+    V3<R> lp = {R(0), R(0), R(0)};
+    if (ob.flags & 4) lp = xf_point(ob.inv, position);                    // spheres, cylinders, cubes, textured planes
+    V3<R> nv;
+    V3<R> tri_color = {R(0), R(0), R(0)};
+    if (type == 0 && !(ob.flags & 2)) {
+        // plane without normal map: object normal (0,1,0) -> world normal is a constant of the
+        // object, normalize(inverseTranspose * (0,1,0)), precomputed on the host (tracer.cl:913, 953-955)
+        nv = {ob.plane_n[0], ob.plane_n[1], ob.plane_n[2]};
+    } else {
+        V3<R> on;
+        if (type == 0) {                                                  // tracer.cl:906-911
+            float3 c = sample_rgba8(P.tex[0], (float)(m_abs(lp.x) * ob.tex_sx_nm), (float)(m_abs(lp.z) * ob.tex_sy_nm), ob.tex_index_nm);
+            on = normalize(V3<R>{R(c.x), R(c.y), R(c.z)});
+        } else if (type == 1) {
+            on = lp;                                                      // tracer.cl:919-920
+        } else if (type == 2) {                                           // tracer.cl:924-932
+            R dist = lp.x * lp.x + lp.z * lp.z;
+            if (dist < R(1) && lp.y >= ob.max_y - eps) on = {R(0), R(1), R(0)};
+            else if (dist < R(1) && lp.y <= ob.min_y + eps) on = {R(0), R(-1), R(0)};
+            else on = {lp.x, R(0), lp.z};
+        } else if (type == 3) {                                           // tracer.cl:938-946
+            R ax = m_abs(lp.x), ay = m_abs(lp.y), az = m_abs(lp.z);
+            R maxc = m_max(m_max(ax, ay), az);
+            if (maxc == ax) on = {lp.x, R(0), R(0)};
+            else if (maxc == ay) on = {R(0), lp.y, R(0)};
+            else on = {R(0), R(0), lp.z};
+        } else {                                                          // tracer.cl:669, 949
+            const V4<R> s0 = ldg4(&P.tri_shade[3 * h.tri]), s1 = ldg4(&P.tri_shade[3 * h.tri + 1]), s2 = ldg4(&P.tri_shade[3 * h.tri + 2]);
+            R w = R(1) - h.u - h.v;
+            on = {s1.x * h.u + s2.x * h.v + s0.x * w, s1.y * h.u + s2.y * h.v + s0.y * w, s1.z * h.u + s2.z * h.v + s0.z * w};
+            tri_color = {s0.w, s1.w, s2.w};
+        }
+        nv = {ob.invt[0] * on.x + ob.invt[1] * on.y + ob.invt[2] * on.z,
+              ob.invt[3] * on.x + ob.invt[4] * on.y + ob.invt[5] * on.z,
+              ob.invt[6] * on.x + ob.invt[7] * on.y + ob.invt[8] * on.z};   // tracer.cl:953-955
+        nv = normalize(nv);
+    }
+    if (dot(eye, nv) < R(0)) nv = nv * R(-1);                                  // tracer.cl:962-964
+    V3<R> over = position + nv * eps;
+    const V3<R> under = position - nv * eps;
+
+    // material branch, tracer.cl:975-1062
+    R cosine = R(1);
+    bool entering = false, exiting = false, reflecting = false;
+    const R refl = ob.reflectivity, ri = ob.refractive_index;
+    bool mirror = false;
+    if (refl != R(0) && R(noise3d<RNG>(fgi, (float)n, (float)s.b)) < refl) {
+        mirror = true;
+    } else if (ri == R(-1)) {                                                 // thin glass
+        if (schlick(eye, nv, R(1), R(1.5)) < R(noise3d<RNG>(fgi, (float)(n * n), (float)s.b))) over = under;
+        else mirror = true;
+    } else if (ri != R(1)) {
+        R rnd = R(noise3d<RNG>(fgi, (float)(n * n), (float)s.b));
+        if (!s.inside) {
+            if (schlick(eye, nv, R(1), ri) < rnd) { rd = refracted(eye, nv, R(1), ri); over = under; s.inside = true; entering = true; }
+            else mirror = true;
+        } else {
+            if (schlick(eye, nv, ri, R(1)) < rnd) { rd = refracted(eye, nv, ri, R(1)); over = under; s.inside = false; exiting = true; }
+            else mirror = true;
+        }
+    } else {                                                                  // diffuse, tracer.cl:348-366
+        R rand1 = R(2) * pi * R(noise3d<RNG>(fgi, (float)s.b, (float)n));
+        R rand2 = R(noise3d<RNG>((float)s.b, (float)n, fgi));
+        R rand2s = m_sqrt(rand2);
+        // u = normalize(cross(axis, n)) with axis = (0,1,0) if |n.x| > 0.1 else (1,0,0); the cross
+        // product with a unit axis is written out (same values: the other terms are exact zeros)
+        const bool ay_axis = m_abs(nv.x) > R(0.1);
+        V3<R> uu = ay_axis ? V3<R>{nv.z, R(0), -nv.x} : V3<R>{R(0), -nv.z, nv.y};
+        uu = normalize(uu);
+        V3<R> vv = cross(nv, uu);
+        R s1, c1;
+        m_sincos_2pi(rand1, &s1, &c1);
+        rd = uu * (c1 * rand2s) + vv * (s1 * rand2s) + nv * m_sqrt(R(1) - rand2);
+        cosine = dot(rd, nv);
+    }
+    if (mirror) {                                                             // tracer.cl:985-988
+        R ds = dot(rd, nv);
+        rd = rd - nv * (R(2) * ds);
+        reflecting = true;
+    }
+    ro = over;
+
+    // surface colour, tracer.cl:1071-1096
+    V3<R> colr, emis;
+    if (type == 4) { colr = tri_color; emis = {R(0), R(0), R(0)}; }
+    else {
+        colr = {ob.color[0], ob.color[1], ob.color[2]};
+        emis = {ob.emission[0], ob.emission[1], ob.emission[2]};
+        if (ob.flags & 1) {
+            if (type == 0) {
+                float3 c = sample_rgba8(P.tex[0], (float)(lp.x * ob.tex_sx), (float)(lp.z * ob.tex_sy), ob.tex_index);
+                colr = {R(c.x), R(c.y), R(c.z)};
+            } else if (type == 1) {                                           // sphericalMap, tracer.cl:178-213
+                R theta = m_atan2(lp.x, lp.z);
+                R radius = sqrt(dot(lp, lp));
+                R phi = m_acos(lp.y / radius);
+                R su = R(1) - (theta / (R(2) * pi) + R(0.5));
+                R sv = R(1) - phi / pi;
+                float3 c = sample_rgba8(P.tex[1], (float)su, (float)(R(1) - sv), ob.tex_index);
+                colr = {R(c.x), R(c.y), R(c.z)};
+            } else if (type == 3) {
+                R cu, cv;
+                cube_uv(lp, cu, cv);
+                float3 c = sample_rgba8(P.tex[2], (float)cu, (float)cv, ob.tex_index);
+                colr = {R(c.x), R(c.y), R(c.z)};
+            }
+        }
+    }
+
+    // fused shading, tracer.cl:1116-1176: refraction bounces are skipped; an emitter adds
+    // mask*emission (or, when hit directly by the camera ray, replaces accum by its colour)
+    if (!(entering || exiting)) {
+        s.accum = s.accum + s.mask * emis;
+        if (emis.x > R(0)) { if (s.b == 0) s.accum = colr; }
+        s.mask = s.mask * colr;
+        s.mask = s.mask * cosine;
+    }
+    if (!entering && !exiting && !reflecting) s.effective++;                    // tracer.cl:1099-1101
+    s.b++;
+    return (ob.emission[0] > R(0)) || !(s.b < 10u && s.effective < 4u);        // tracer.cl:1107, 884
+}
+
+// Frame geometry of a thread: a warp covers an 8x4 pixel tile.
+struct PixelSlot { int lx, ly, gy; bool has_pixel; };
+template <typename R> __device__ __forceinline__ PixelSlot pixel_slot(const Params<R>& P) {
     const int W = P.cam.width;
     const int tiles_x = (W + kTileW - 1) / kTileW;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int lx = (warp % tiles_x) * kTileW + (lane & (kTileW - 1));
-    const int ly = (warp / tiles_x) * kTileH + (lane / kTileW);
-    // Lanes without a pixel stay in the loop (idle): the BVH walk is warp-cooperative and uses all 32 lanes.
-    const bool has_pixel = lx < W && ly < P.rows;
-    const int gy = has_pixel ? P.row_map[ly] : 0;
-    const int slice = blockIdx.y;
+    PixelSlot s;
+    s.lx = (warp % tiles_x) * kTileW + (lane & (kTileW - 1));
+    s.ly = (warp / tiles_x) * kTileH + (lane / kTileW);
+    s.has_pixel = s.lx < W && s.ly < P.rows;
+    s.gy = s.has_pixel ? P.row_map[s.ly] : 0;
+    return s;
+}
 
-    const R eps = P.eps, pi = P.pi;
+template <typename R> __device__ __forceinline__ void store_pixel(const Params<R>& P, const PixelSlot& px, int slice, double col_r, double col_g, double col_b) {
+    const size_t pix = (size_t)px.ly * P.cam.width + px.lx;
+    if (P.slices == 1 && !P.raw_sums) {
+        const double wgt = 1.0 / (double)P.samples;                                  // tracer.cl:837, 1184-1187
+        double4* o = reinterpret_cast<double4*>(P.out) + pix;
+        *o = make_double4(col_r * wgt, col_g * wgt, col_b * wgt, 1.0);
+    } else {
+        double4* o = reinterpret_cast<double4*>(P.out) + ((size_t)slice * P.rows * P.cam.width + pix);
+        *o = make_double4(col_r, col_g, col_b, 0.0);
+    }
+}
+
+// ---- kernel for scenes without meshes ------------------------------------------------------------
+template <typename R, int RNG>
+__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS)) trace_kernel(const __grid_constant__ Params<R> P) {
+    const PixelSlot px = pixel_slot(P);
+    const int W = P.cam.width;
+    const int slice = blockIdx.y;
     const unsigned samples = (unsigned)P.samples;
-    const double seed = has_pixel ? P.seeds[(size_t)gy * W + lx] : 0.0;
+    const double seed = px.has_pixel ? P.seeds[(size_t)px.gy * W + px.lx] : 0.0;
     const float fgi = (float)(seed / (double)P.n_objects);     // tracer.cl:840
     const float fgi2 = (float)(seed / (double)samples);        // tracer.cl:841
-
-    const R px = R(lx), py = R(gy);
+    const R fx = R(px.lx), fy = R(px.gy);
     const V3<R> cam_origin = {P.cam.inv[3], P.cam.inv[7], P.cam.inv[11]};   // inverse * (0,0,0,1)
 
     double col_r = 0.0, col_g = 0.0, col_b = 0.0;
-
-    // per-path state
-    unsigned n = (unsigned)(P.sample_begin + slice);   // sample index (tracer.cl:867)
+    Path<R> s;
+    s.n = (unsigned)(P.sample_begin + slice);
     const unsigned n_end = (unsigned)P.sample_end;      // == samples unless a caller renders a sample range
-    unsigned b = 0, effective = 0;     // bounce counters (tracer.cl:873-884)
-    bool inside = false;
+    s.b = 0; s.effective = 0; s.inside = false;
+    s.ro = {R(0), R(0), R(0)}; s.rd = {R(0), R(0), R(0)};
+    s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
     bool fresh = true;                 // need a new camera ray
-    bool live = has_pixel;             // false once this lane has finished all its samples
-    V3<R> ro = {R(0), R(0), R(0)}, rd = {R(0), R(0), R(0)};
-    V3<R> mask = {R(1), R(1), R(1)}, accum = {R(0), R(0), R(0)};
+    bool live = px.has_pixel;          // false once this lane has finished all its samples
 
     // Camera rays are generated one path AHEAD and parked in registers.  Generation runs only when
     // some lane needs a ray it does not have; at that moment every lane without a parked ray makes
@@ -586,185 +798,183 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     bool have_next = false;
 
     while (true) {
-        if (fresh && n >= n_end) live = false;
+        if (fresh && s.n >= n_end) live = false;
         if (!__any_sync(kFullMask, live)) break;                 // the warp leaves together
         const bool starved = fresh && live && !have_next;
         if (__any_sync(kFullMask, starved)) {
-            const unsigned gn = fresh ? n : n + (unsigned)P.slices;    // the sample this lane will start next
+            const unsigned gn = fresh ? s.n : s.n + (unsigned)P.slices;    // the sample this lane will start next
             if (live && !have_next && gn < n_end) {
-                // rayForPixel, tracer.cl:745-779
-                float jx = noise3d<RNG>(fgi, (float)gn, fgi2);
-                float jy = noise3d<RNG>(fgi, fgi2, (float)gn);
-                R xo = P.cam.pixel_size * (px + R(jx));
-                R yo = P.cam.pixel_size * (py + R(jy));
-                V3<R> in_view = {P.cam.half_width - xo, P.cam.half_height - yo, R(-1)};
-                V3<R> pixel = xf_point(P.cam.inv, in_view);
-                nxo = cam_origin;
-                nxd = normalize(pixel - nxo);
-                if (P.lens != nullptr) {                                                          // aperture != 0
-                    V3<R> pos = nxo + nxd * P.cam.focal_length;
-                    R sx = ldg1(&P.lens[2 * gn]), sy = ldg1(&P.lens[2 * gn + 1]);                   // NaN at sample 0 when samples >= 3: kept
-                    V3<R> no = {nxo.x + sy * P.cam.aperture, nxo.y + sx * P.cam.aperture, nxo.z}; // x/y swap as upstream
-                    nxd = pos - no;                                                               // left unnormalised
-                    nxo = no;
-                }
+                camera_ray<R, RNG>(P, fx, fy, fgi, fgi2, gn, cam_origin, nxo, nxd);
                 have_next = true;
             }
         }
         if (fresh && live) {
-            ro = nxo; rd = nxd; have_next = false;
-            b = 0; effective = 0; inside = false;
-            mask = {R(1), R(1), R(1)}; accum = {R(0), R(0), R(0)};
+            s.ro = nxo; s.rd = nxd; have_next = false;
+            s.b = 0; s.effective = 0; s.inside = false;
+            s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
             fresh = false;
         }
 
         Hit<R> h;
-        closest_hit<R, GROUPS>(P, ro, rd, live, lane, h);
+        closest_analytic<R>(P, s.ro, s.rd, h);
 
         bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
-        if (live && h.obj >= 0) {
-            const DObjShade<R>& ob = P.shade[h.obj];
-            const int type = ob.type;
-            V3<R> position = ro + rd * h.t;
-            V3<R> eye = {-rd.x, -rd.y, -rd.z};
-            V3<R> lp = {R(0), R(0), R(0)};
-            if (ob.flags & 4) lp = xf_point(ob.inv, position);                    // spheres, cylinders, cubes, textured planes
-            V3<R> nv;
-            V3<R> tri_color = {R(0), R(0), R(0)};
-            if (type == 0 && !(ob.flags & 2)) {
-                // plane without normal map: object normal (0,1,0) -> world normal is a constant of the
-                // object, normalize(inverseTranspose * (0,1,0)), precomputed on the host (tracer.cl:913, 953-955)
-                nv = {ob.plane_n[0], ob.plane_n[1], ob.plane_n[2]};
-            } else {
-                V3<R> on;
-                if (type == 0) {                                                  // tracer.cl:906-911
-                    float3 c = sample_rgba8(P.tex[0], (float)(m_abs(lp.x) * ob.tex_sx_nm), (float)(m_abs(lp.z) * ob.tex_sy_nm), ob.tex_index_nm);
-                    on = normalize(V3<R>{R(c.x), R(c.y), R(c.z)});
-                } else if (type == 1) {
-                    on = lp;                                                      // tracer.cl:919-920
-                } else if (type == 2) {                                           // tracer.cl:924-932
-                    R dist = lp.x * lp.x + lp.z * lp.z;
-                    if (dist < R(1) && lp.y >= ob.max_y - eps) on = {R(0), R(1), R(0)};
-                    else if (dist < R(1) && lp.y <= ob.min_y + eps) on = {R(0), R(-1), R(0)};
-                    else on = {lp.x, R(0), lp.z};
-                } else if (type == 3) {                                           // tracer.cl:938-946
-                    R ax = m_abs(lp.x), ay = m_abs(lp.y), az = m_abs(lp.z);
-                    R maxc = m_max(m_max(ax, ay), az);
-                    if (maxc == ax) on = {lp.x, R(0), R(0)};
-                    else if (maxc == ay) on = {R(0), lp.y, R(0)};
-                    else on = {R(0), R(0), lp.z};
-                } else {                                                          // tracer.cl:669, 949
-                    const V4<R> s0 = ldg4(&P.tri_shade[3 * h.tri]), s1 = ldg4(&P.tri_shade[3 * h.tri + 1]), s2 = ldg4(&P.tri_shade[3 * h.tri + 2]);
-                    R w = R(1) - h.u - h.v;
-                    on = {s1.x * h.u + s2.x * h.v + s0.x * w, s1.y * h.u + s2.y * h.v + s0.y * w, s1.z * h.u + s2.z * h.v + s0.z * w};
-                    tri_color = {s0.w, s1.w, s2.w};
-                }
-                nv = {ob.invt[0] * on.x + ob.invt[1] * on.y + ob.invt[2] * on.z,
-                      ob.invt[3] * on.x + ob.invt[4] * on.y + ob.invt[5] * on.z,
-                      ob.invt[6] * on.x + ob.invt[7] * on.y + ob.invt[8] * on.z};   // tracer.cl:953-955
-                nv = normalize(nv);
-            }
-            if (dot(eye, nv) < R(0)) nv = nv * R(-1);                                  // tracer.cl:962-964
-            V3<R> over = position + nv * eps;
-            const V3<R> under = position - nv * eps;
-
-            // material branch, tracer.cl:975-1062
-            R cosine = R(1);
-            bool entering = false, exiting = false, reflecting = false;
-            const R refl = ob.reflectivity, ri = ob.refractive_index;
-            bool mirror = false;
-            if (refl != R(0) && R(noise3d<RNG>(fgi, (float)n, (float)b)) < refl) {
-                mirror = true;
-            } else if (ri == R(-1)) {                                                 // thin glass
-                if (schlick(eye, nv, R(1), R(1.5)) < R(noise3d<RNG>(fgi, (float)(n * n), (float)b))) over = under;
-                else mirror = true;
-            } else if (ri != R(1)) {
-                R rnd = R(noise3d<RNG>(fgi, (float)(n * n), (float)b));
-                if (!inside) {
-                    if (schlick(eye, nv, R(1), ri) < rnd) { rd = refracted(eye, nv, R(1), ri); over = under; inside = true; entering = true; }
-                    else mirror = true;
-                } else {
-                    if (schlick(eye, nv, ri, R(1)) < rnd) { rd = refracted(eye, nv, ri, R(1)); over = under; inside = false; exiting = true; }
-                    else mirror = true;
-                }
-            } else {                                                                  // diffuse, tracer.cl:348-366
-                R rand1 = R(2) * pi * R(noise3d<RNG>(fgi, (float)b, (float)n));
-                R rand2 = R(noise3d<RNG>((float)b, (float)n, fgi));
-                R rand2s = m_sqrt(rand2);
-                // u = normalize(cross(axis, n)) with axis = (0,1,0) if |n.x| > 0.1 else (1,0,0); the cross
-                // product with a unit axis is written out (same values: the other terms are exact zeros)
-                const bool ay_axis = m_abs(nv.x) > R(0.1);
-                V3<R> uu = ay_axis ? V3<R>{nv.z, R(0), -nv.x} : V3<R>{R(0), -nv.z, nv.y};
-                uu = normalize(uu);
-                V3<R> vv = cross(nv, uu);
-                R s1, c1;
-                m_sincos_2pi(rand1, &s1, &c1);
-                rd = uu * (c1 * rand2s) + vv * (s1 * rand2s) + nv * m_sqrt(R(1) - rand2);
-                cosine = dot(rd, nv);
-            }
-            if (mirror) {                                                             // tracer.cl:985-988
-                R ds = dot(rd, nv);
-                rd = rd - nv * (R(2) * ds);
-                reflecting = true;
-            }
-            ro = over;
-
-            // surface colour, tracer.cl:1071-1096
-            V3<R> colr, emis;
-            if (type == 4) { colr = tri_color; emis = {R(0), R(0), R(0)}; }
-            else {
-                colr = {ob.color[0], ob.color[1], ob.color[2]};
-                emis = {ob.emission[0], ob.emission[1], ob.emission[2]};
-                if (ob.flags & 1) {
-                    if (type == 0) {
-                        float3 c = sample_rgba8(P.tex[0], (float)(lp.x * ob.tex_sx), (float)(lp.z * ob.tex_sy), ob.tex_index);
-                        colr = {R(c.x), R(c.y), R(c.z)};
-                    } else if (type == 1) {                                           // sphericalMap, tracer.cl:178-213
-                        R theta = m_atan2(lp.x, lp.z);
-                        R radius = sqrt(dot(lp, lp));
-                        R phi = m_acos(lp.y / radius);
-                        R su = R(1) - (theta / (R(2) * pi) + R(0.5));
-                        R sv = R(1) - phi / pi;
-                        float3 c = sample_rgba8(P.tex[1], (float)su, (float)(R(1) - sv), ob.tex_index);
-                        colr = {R(c.x), R(c.y), R(c.z)};
-                    } else if (type == 3) {
-                        R cu, cv;
-                        cube_uv(lp, cu, cv);
-                        float3 c = sample_rgba8(P.tex[2], (float)cu, (float)cv, ob.tex_index);
-                        colr = {R(c.x), R(c.y), R(c.z)};
-                    }
-                }
-            }
-
-            // fused shading, tracer.cl:1116-1176: refraction bounces are skipped; an emitter adds
-            // mask*emission (or, when hit directly by the camera ray, replaces accum by its colour)
-            if (!(entering || exiting)) {
-                accum = accum + mask * emis;
-                if (emis.x > R(0)) { if (b == 0) accum = colr; }
-                mask = mask * colr;
-                mask = mask * cosine;
-            }
-            if (!entering && !exiting && !reflecting) effective++;                    // tracer.cl:1099-1101
-            b++;
-            done = (ob.emission[0] > R(0)) || !(b < 10u && effective < 4u);           // tracer.cl:1107, 884
-        }
+        if (live && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);
         if (done) {
-            col_r += (double)accum.x; col_g += (double)accum.y; col_b += (double)accum.z;   // tracer.cl:1179
-            n += (unsigned)P.slices;
+            col_r += (double)s.accum.x; col_g += (double)s.accum.y; col_b += (double)s.accum.z;   // tracer.cl:1179
+            s.n += (unsigned)P.slices;
             fresh = true;
         }
     }
+    if (px.has_pixel) store_pixel(P, px, slice, col_r, col_g, col_b);
+}
 
-    if (!has_pixel) return;
-    const size_t pix = (size_t)ly * W + lx;
-    if (P.slices == 1 && !P.raw_sums) {
-        const double wgt = 1.0 / (double)samples;                                    // tracer.cl:837, 1184-1187
-        double4* o = reinterpret_cast<double4*>(P.out) + pix;
-        *o = make_double4(col_r * wgt, col_g * wgt, col_b * wgt, 1.0);
-    } else {
-        double4* o = reinterpret_cast<double4*>(P.out) + ((size_t)slice * P.rows * W + pix);
-        *o = make_double4(col_r, col_g, col_b, 0.0);
+// ---- kernel for scenes with meshes ---------------------------------------------------------------
+// Same segment loop, but the BVH walk is taken out of it.  Only a fraction of a warp's rays reach a mesh
+// on any given segment (ncu on the teapot scene: ~4 of 32 lanes in the walk of the previous design), so
+// walking in place leaves most lanes idle.  Instead a thread whose ray needs a mesh PARKS it in a
+// block-wide queue in shared memory and waits; the other lanes carry on with their paths.  When a
+// warp's worth of rays is queued (or nothing else can run) the block makes one BVH pass: thread k walks
+// queued ray k -- per-lane traversal of the rebuilt tree with full warps -- and writes the result to
+// the owner's slot; the owners pick their hits up and shade in the same iteration as everybody else.
+template <typename R> struct MeshShared {
+    // dynamic shared memory, T = block size:  int stack[kMeshStack][T];  R ray[7][T] (o, d, best t);
+    // int ent[2][T] (best object, owner);  R res[3][T] (t, u, v);  int resi[2][T] (object, slot);
+    // int2 tally[2][T/32];  int count
+    static __host__ __device__ size_t bytes(int T) {
+        return size_t(kMeshStack) * T * 4 + size_t(7) * T * sizeof(R) + size_t(2) * T * 4 + size_t(3) * T * sizeof(R) + size_t(2) * T * 4 +
+               size_t(2) * (T / 32) * 8 + 16;
     }
+};
+
+#ifndef PTK_MESH_MIN_BLOCKS
+#define PTK_MESH_MIN_BLOCKS 6
+#endif
+#ifndef PTK_MESH_MIN_BLOCKS_F64
+#define PTK_MESH_MIN_BLOCKS_F64 3
+#endif
+
+template <typename R, int RNG, int T>
+__global__ void __launch_bounds__(T, ((sizeof(R) == 8 ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MESH_MIN_BLOCKS) * 128) / T)
+trace_mesh_kernel(const __grid_constant__ Params<R> P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* const q_ray = reinterpret_cast<R*>(smem_raw);                       // [7][T]
+    R* const q_res = q_ray + 7 * T;                                        // [3][T]
+    int* const q_stack = reinterpret_cast<int*>(q_res + 3 * T);            // [kMeshStack][T]
+    int* const q_ent = q_stack + kMeshStack * T;                           // [2][T]
+    int* const q_resi = q_ent + 2 * T;                                     // [2][T]
+    int2* const q_tally = reinterpret_cast<int2*>(q_resi + 2 * T);         // [2][T/32]
+    int* const q_count = reinterpret_cast<int*>(q_tally + 2 * (T / 32));
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) *q_count = 0;
+    __syncthreads();
+
+    const PixelSlot px = pixel_slot(P);
+    const int W = P.cam.width;
+    const int slice = blockIdx.y;
+    const unsigned samples = (unsigned)P.samples;
+    const double seed = px.has_pixel ? P.seeds[(size_t)px.gy * W + px.lx] : 0.0;
+    const float fgi = (float)(seed / (double)P.n_objects);     // tracer.cl:840
+    const float fgi2 = (float)(seed / (double)samples);        // tracer.cl:841
+    const R fx = R(px.lx), fy = R(px.gy);
+    const V3<R> cam_origin = {P.cam.inv[3], P.cam.inv[7], P.cam.inv[11]};
+
+    double col_r = 0.0, col_g = 0.0, col_b = 0.0;
+    Path<R> s;
+    s.n = (unsigned)(P.sample_begin + slice);
+    const unsigned n_end = (unsigned)P.sample_end;
+    s.b = 0; s.effective = 0; s.inside = false;
+    s.ro = {R(0), R(0), R(0)}; s.rd = {R(0), R(0), R(0)};
+    s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
+    bool fresh = true, live = px.has_pixel;
+    bool waiting = false;              // this thread's ray is parked in the queue
+    V3<R> nxo = cam_origin, nxd = {R(0), R(0), R(0)};
+    bool have_next = false;
+    Hit<R> h;
+    h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
+    int queued = 0;                    // rays in the queue (same value in every thread of the block)
+    int parity = 0;
+
+    while (true) {
+        if (fresh && s.n >= n_end) live = false;
+        const bool starved = fresh && live && !have_next;
+        if (__any_sync(kFullMask, starved)) {
+            const unsigned gn = fresh ? s.n : s.n + (unsigned)P.slices;
+            if (live && !have_next && gn < n_end) {
+                camera_ray<R, RNG>(P, fx, fy, fgi, fgi2, gn, cam_origin, nxo, nxd);
+                have_next = true;
+            }
+        }
+        if (fresh && live) {
+            s.ro = nxo; s.rd = nxd; have_next = false;
+            s.b = 0; s.effective = 0; s.inside = false;
+            s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
+            fresh = false;
+        }
+
+        // analytic objects for every lane that has a ray to trace; then: does a mesh have to be walked?
+        const bool run = live && !waiting;
+        Hit<R> hn;
+        closest_analytic<R>(P, s.ro, s.rd, hn);
+        if (run) h = hn;
+        const bool want = run && mesh_wanted<R>(P, s.ro, s.rd, h.t);
+        const unsigned wm = __ballot_sync(kFullMask, want);
+        if (wm) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(q_count, __popc(wm));
+            base = __shfl_sync(kFullMask, base, 0);
+            if (want) {
+                const int e = base + __popc(wm & ((1u << lane) - 1u));
+                q_ray[0 * T + e] = s.ro.x; q_ray[1 * T + e] = s.ro.y; q_ray[2 * T + e] = s.ro.z;
+                q_ray[3 * T + e] = s.rd.x; q_ray[4 * T + e] = s.rd.y; q_ray[5 * T + e] = s.rd.z;
+                q_ray[6 * T + e] = h.t;
+                q_ent[0 * T + e] = h.obj; q_ent[1 * T + e] = tid;
+                waiting = true;
+            }
+        }
+        const unsigned rm = __ballot_sync(kFullMask, live && !waiting);
+        if (lane == 0) q_tally[parity * (T / 32) + wid] = make_int2(__popc(wm), rm != 0u);
+        __syncthreads();                                             // ---- barrier A
+        bool runnable = false;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) { const int2 v = q_tally[parity * (T / 32) + w]; queued += v.x; runnable = runnable || v.y != 0; }
+        parity ^= 1;
+        if (queued == 0 && !runnable) break;                         // every thread of the block is finished
+        bool resolved = false;
+        if (queued > 0 && (queued >= P.drain_threshold || !runnable)) {
+            if (tid == 0) *q_count = 0;                              // nobody enqueues before barrier B
+            if (tid < queued) {
+                const V3<R> wo = {q_ray[0 * T + tid], q_ray[1 * T + tid], q_ray[2 * T + tid]};
+                const V3<R> wd = {q_ray[3 * T + tid], q_ray[4 * T + tid], q_ray[5 * T + tid]};
+                R ct = q_ray[6 * T + tid], cu = R(0), cv = R(0);
+                int cobj = q_ent[0 * T + tid], cslot = -1;
+                const int owner = q_ent[1 * T + tid];
+                mesh_walk<R>(P, wo, wd, ct, cobj, cslot, cu, cv, q_stack + tid, T);
+                q_res[0 * T + owner] = ct; q_res[1 * T + owner] = cu; q_res[2 * T + owner] = cv;
+                q_resi[0 * T + owner] = cobj; q_resi[1 * T + owner] = cslot;
+            }
+            __syncthreads();                                         // ---- barrier B
+            queued = 0;
+            if (waiting) {
+                if (q_resi[1 * T + tid] >= 0) {
+                    h.t = q_res[0 * T + tid]; h.u = q_res[1 * T + tid]; h.v = q_res[2 * T + tid];
+                    h.obj = q_resi[0 * T + tid]; h.tri = q_resi[1 * T + tid];
+                }
+                waiting = false; resolved = true;
+            }
+        }
+
+        const bool ready = live && !waiting && (run || resolved);
+        bool done = ready;                       // a miss ends the path
+        if (ready && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);
+        if (done) {
+            col_r += (double)s.accum.x; col_g += (double)s.accum.y; col_b += (double)s.accum.z;
+            s.n += (unsigned)P.slices;
+            fresh = true;
+        }
+    }
+    if (px.has_pixel) store_pixel(P, px, slice, col_r, col_g, col_b);
 }
 
 // Sums the per-slice partials in slice order (deterministic) and applies the 1/samples weight.

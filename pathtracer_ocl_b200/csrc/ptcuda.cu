@@ -60,123 +60,220 @@ template <typename R> struct HostScene {
     ptk::DRun runs[ptk::kMaxObjects];
     int n_runs = 0;
     std::vector<ptk::DObjShade<R>> shade;
+    std::vector<ptk::DMesh<R>> mesh;              // one per object
     std::vector<R> lens;       // sunflower lens points, 2 per sample (empty without depth of field)
-    std::vector<ptk::V4<R>> node_lo, node_hi;
-    std::vector<int4> node_meta;
-    std::vector<ptk::V4<R>> chunk_lo, chunk_hi;   // bounding box per 32-slot triangle chunk
-    std::vector<ptk::V4<R>> tri_test, tri_shade;
-    std::vector<int> tri_orig;                    // slot -> index in the caller's triangle buffer
+    std::vector<ptk::V4<R>> node_lo, node_hi;     // reference BVH boxes in the reference's visiting order
+    std::vector<int> node_parent;
+    std::vector<ptk::V4<R>> bvh_a, bvh_b, bvh_c;  // rebuilt BVH: child boxes per node
+    std::vector<int2> bvh_child;
+    std::vector<ptk::V4<R>> tri_test, tri_shade;  // 3 records per slot, slots in leaf order
+    std::vector<int2> tri_info;                   // slot -> (rank in the reference's recording order, reference node)
     ptk::DCam<R> cam;
+    int mesh_depth = 0;
 };
 
-// Re-emit the BVH below every root child of a group object in traversal order: node, then the
-// subtree of children[0], then the subtree of children[1] -- the visiting order of the reference's
-// stack walk (tracer.cl:624-714; "children[k] > 0" means "has child", scene.go:139-152).  Each
-// node's triangles are appended contiguously as it is emitted, and `skip` points past its subtree.
-// True extent of the triangles below a node, and whether every node box on the way contained it.  The
-// distance / behind-the-ray culls of the device walk rely on "a node's box contains its subtree", which
-// the reference's Divide()+Bounds() guarantee; a caller-supplied BVH that violates it is still rendered
-// correctly, just without those culls (DObjHot.pad bit 1).
-struct SubtreeInfo {
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    bool consistent = true;
-    void add(const double* p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
-    void merge(const SubtreeInfo& o) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], o.lo[a]); hi[a] = std::max(hi[a], o.hi[a]); } consistent = consistent && o.consistent; }
-};
+// A triangle of a group object as the reference reaches it: `ref_node` is the (re-emitted) node that
+// holds it, `rank` its position in the reference's recording order (root children in order, each walked
+// node-first, then children[0]'s subtree, then children[1]'s: tracer.cl:624-714; a node's triangles by
+// increasing offset, :637).
+struct RefTri { int src, ref_node, rank; };
 
+// Re-emit the caller's BVH below one root child in the reference's visiting order, keeping only what the
+// device needs to answer "does the reference test the triangles of this node for this ray": the boxes
+// (converted to R exactly as the kernel will see them) and the parent links.  `nested` is cleared when a
+// child box is not contained in its parent's box -- then the device checks the whole chain per candidate.
 template <typename R>
-void emit_subtree(const ptw_group* groups, int n_groups, const ptw_triangle* tris, int n_tris, int g, int depth, HostScene<R>& out, SubtreeInfo& info) {
+void collect_reference_nodes(const ptw_group* groups, int n_groups, int n_tris, int g, int parent, int depth, HostScene<R>& out,
+                             std::vector<RefTri>& list, bool& nested) {
     if (g < 0 || g >= n_groups) fail("BVH node index %d out of range (%d groups)", g, n_groups);
     if (depth > PTW_BVH_STACK) fail("BVH deeper than %d levels (the reference's traversal stack, tracer.cl:624)", PTW_BVH_STACK);
     const ptw_group& s = groups[g];
     const int me = int(out.node_lo.size());
     out.node_lo.push_back({R(s.bb_min[0]), R(s.bb_min[1]), R(s.bb_min[2]), R(0)});
     out.node_hi.push_back({R(s.bb_max[0]), R(s.bb_max[1]), R(s.bb_max[2]), R(0)});
-    const int count = s.tri_count > 0 ? s.tri_count : 0;
-    if (count > 0 && (s.tri_offset < 0 || s.tri_offset + s.tri_count > n_tris)) fail("BVH node %d references triangles outside the buffer", g);
-    // The node's own triangles are regrouped into CHUNKS of 32 slots (one warp step each): sorted along a
-    // Morton curve of their centroids so a chunk is spatially compact, each chunk with its own bounding
-    // box.  The reference tests every triangle of a visited node; a ray that misses a chunk's box cannot
-    // hit any triangle inside it, so skipping the chunk changes no result.  Unused slots hold a degenerate
-    // triangle (zero edges -> |det| < EPSILON -> rejected like upstream).  `tri_orig` keeps each slot's
-    // index in the caller's triangle buffer: ties between equal t go to the lowest ORIGINAL index, the
-    // triangle the reference would have recorded first.
-    int4 meta;
-    meta.x = int(out.chunk_lo.size());
-    meta.y = 0; meta.z = 0; meta.w = count;
-    if (count > 0) {
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        std::vector<std::array<double, 3>> cen;
-        cen.resize(static_cast<size_t>(count));
-        for (int k = 0; k < count; ++k) {
-            const ptw_triangle& t = tris[s.tri_offset + k];
-            for (int a = 0; a < 3; ++a) {
-                cen[size_t(k)][size_t(a)] = (t.p1[a] + t.p2[a] + t.p3[a]) / 3.0;
-                lo[a] = std::min(lo[a], cen[size_t(k)][size_t(a)]); hi[a] = std::max(hi[a], cen[size_t(k)][size_t(a)]);
-            }
+    out.node_parent.push_back(parent);
+    if (parent >= 0) {
+        const ptk::V4<R>&plo = out.node_lo[size_t(parent)], &phi = out.node_hi[size_t(parent)], &lo = out.node_lo[size_t(me)], &hi = out.node_hi[size_t(me)];
+        if (!(plo.x <= lo.x && plo.y <= lo.y && plo.z <= lo.z && phi.x >= hi.x && phi.y >= hi.y && phi.z >= hi.z)) nested = false;
+    }
+    if (s.tri_count > 0) {
+        if (s.tri_offset < 0 || s.tri_offset + s.tri_count > n_tris) fail("BVH node %d references triangles outside the buffer", g);
+        for (int k = 0; k < s.tri_count; ++k) list.push_back(RefTri{s.tri_offset + k, me, int(list.size())});
+    }
+    for (int k = 0; k < 2; ++k)
+        if (s.children[k] > 0) collect_reference_nodes(groups, n_groups, n_tris, s.children[k], me, depth + 1, out, list, nested);
+}
+
+// ---- rebuilt BVH ---------------------------------------------------------------------------------
+// Binary BVH over the triangles of one group object: binned surface-area heuristic, leaves of <= 4
+// triangles, built in double.  It is an INDEX only -- which triangles may be hit is still decided by the
+// reference's own arithmetic on the device -- so the one requirement is that a node's stored box
+// contains its triangles with room for the rounding of the device's slab test: boxes are padded.
+struct Box3 {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    void add(const double* p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void merge(const Box3& o) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], o.lo[a]); hi[a] = std::max(hi[a], o.hi[a]); } }
+    bool empty() const { return lo[0] > hi[0]; }
+    double half_area() const {
+        if (empty()) return 0.0;
+        const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return x * y + y * z + z * x;
+    }
+};
+struct BuildPrim { Box3 box; double c[3]; RefTri ref; };
+
+template <typename R> void padded(const Box3& b, R* lo, R* hi) {
+    for (int a = 0; a < 3; ++a) {
+        const double pad = 1e-4 * (b.hi[a] - b.lo[a]) + 2e-6 * std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])) + 1e-9;
+        lo[a] = R(b.lo[a] - pad); hi[a] = R(b.hi[a] + pad);
+        if (double(lo[a]) > b.lo[a] - 0.5 * pad) lo[a] = std::nextafter(lo[a], R(-1e30));   // rounding to R went inward
+        if (double(hi[a]) < b.hi[a] + 0.5 * pad) hi[a] = std::nextafter(hi[a], R(1e30));
+    }
+}
+
+template <typename R> struct BvhBuilder {
+    const ptw_triangle* tris;
+    HostScene<R>& out;
+    std::vector<BuildPrim>& prims;
+    int max_depth = 0;
+    static constexpr int kBins = 32, kMaxLeaf = 4, kSahDepth = 20;
+
+    int make_leaf(int begin, int end) {
+        const int first = int(out.tri_info.size());
+        for (int i = begin; i < end; ++i) {
+            const RefTri& r = prims[size_t(i)].ref;
+            const ptw_triangle& t = tris[r.src];
+            out.tri_test.push_back({R(t.p1[0]), R(t.p1[1]), R(t.p1[2]), R(t.e1[0])});
+            out.tri_test.push_back({R(t.e1[1]), R(t.e1[2]), R(t.e2[0]), R(t.e2[1])});
+            out.tri_test.push_back({R(t.e2[2]), R(0), R(0), R(0)});
+            out.tri_shade.push_back({R(t.n1[0]), R(t.n1[1]), R(t.n1[2]), R(t.color[0])});
+            out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
+            out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
+            out.tri_info.push_back(make_int2(r.rank, r.ref_node));
         }
-        auto spread = [](uint32_t v) { uint64_t x = v & 0x1fffff; x = (x | x << 32) & 0x1f00000000ffffULL; x = (x | x << 16) & 0x1f0000ff0000ffULL;
-                                       x = (x | x << 8) & 0x100f00f00f00f00fULL; x = (x | x << 4) & 0x10c30c30c30c30c3ULL; x = (x | x << 2) & 0x1249249249249249ULL; return x; };
-        std::vector<std::pair<uint64_t, int>> order(static_cast<size_t>(count));
-        for (int k = 0; k < count; ++k) {
-            uint64_t code = 0;
+        if (first >= (1 << 27)) fail("too many triangles");
+        return ~((first << 3) | (end - begin));
+    }
+
+    // Builds the subtree over prims[begin, end); returns its child code (node index, or ~leaf code) and box.
+    int build(int begin, int end, int depth, Box3& box) {
+        max_depth = std::max(max_depth, depth);
+        box = Box3();
+        Box3 cb;
+        for (int i = begin; i < end; ++i) { box.merge(prims[size_t(i)].box); cb.add(prims[size_t(i)].c); }
+        const int count = end - begin;
+        if (count <= 1) return make_leaf(begin, end);
+        int mid = -1;
+        const double ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
+        if (depth < kSahDepth && (ext[0] > 0 || ext[1] > 0 || ext[2] > 0)) {
+            double best = 1e300; int best_axis = -1, best_bin = -1;
             for (int a = 0; a < 3; ++a) {
-                const double ext = hi[a] - lo[a];
-                const double f = ext > 0 ? (cen[size_t(k)][size_t(a)] - lo[a]) / ext : 0.0;
-                code |= spread(uint32_t(f * 2097151.0)) << a;
-            }
-            order[size_t(k)] = {code, k};
-        }
-        std::sort(order.begin(), order.end());
-        for (int c0 = 0; c0 < count; c0 += 32) {
-            double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
-            for (int k = 0; k < 32; ++k) {
-                if (c0 + k < count) {
-                    const int src = s.tri_offset + order[size_t(c0 + k)].second;
-                    const ptw_triangle& t = tris[src];
-                    for (int a = 0; a < 3; ++a) {
-                        blo[a] = std::min(blo[a], std::min(t.p1[a], std::min(t.p2[a], t.p3[a])));
-                        bhi[a] = std::max(bhi[a], std::max(t.p1[a], std::max(t.p2[a], t.p3[a])));
-                    }
-                    out.tri_test.push_back({R(t.p1[0]), R(t.p1[1]), R(t.p1[2]), R(t.e1[0])});
-                    out.tri_test.push_back({R(t.e1[1]), R(t.e1[2]), R(t.e2[0]), R(t.e2[1])});
-                    out.tri_test.push_back({R(t.e2[2]), R(0), R(0), R(0)});
-                    out.tri_shade.push_back({R(t.n1[0]), R(t.n1[1]), R(t.n1[2]), R(t.color[0])});
-                    out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
-                    out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
-                    out.tri_orig.push_back(src);
-                    info.add(t.p1); info.add(t.p2); info.add(t.p3);
-                } else {
-                    for (int q = 0; q < 3; ++q) { out.tri_test.push_back({R(0), R(0), R(0), R(0)}); out.tri_shade.push_back({R(0), R(0), R(0), R(0)}); }
-                    out.tri_orig.push_back(0x7fffffff);
+                if (!(ext[a] > 0)) continue;
+                Box3 bb[kBins]; int bn[kBins] = {0};
+                const double scale = double(kBins) / ext[a];
+                for (int i = begin; i < end; ++i) {
+                    int k = int((prims[size_t(i)].c[a] - cb.lo[a]) * scale);
+                    k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                    bb[k].merge(prims[size_t(i)].box); bn[k]++;
+                }
+                double right_area[kBins]; int right_n[kBins];
+                Box3 acc; int n = 0;
+                for (int k = kBins - 1; k > 0; --k) { acc.merge(bb[k]); n += bn[k]; right_area[k] = acc.half_area(); right_n[k] = n; }
+                acc = Box3(); n = 0;
+                for (int k = 0; k < kBins - 1; ++k) {
+                    acc.merge(bb[k]); n += bn[k];
+                    if (n == 0 || right_n[k + 1] == 0) continue;
+                    const double cost = acc.half_area() * n + right_area[k + 1] * right_n[k + 1];
+                    if (cost < best) { best = cost; best_axis = a; best_bin = k; }
                 }
             }
-            // pad the chunk box: the cull must never reject a ray that the exact triangle test would accept
-            R plo[3], phi[3];
-            for (int a = 0; a < 3; ++a) {
-                const double pad = 1e-4 * (bhi[a] - blo[a]) + 1e-6 * std::max(std::fabs(blo[a]), std::fabs(bhi[a])) + 1e-9;
-                plo[a] = R(blo[a] - pad); phi[a] = R(bhi[a] + pad);
-                if (double(plo[a]) > blo[a] - 0.5 * pad) plo[a] = std::nextafter(plo[a], R(-1e30));   // float rounding went inward
-                if (double(phi[a]) < bhi[a] + 0.5 * pad) phi[a] = std::nextafter(phi[a], R(1e30));
+            // leaf cost `count` vs one more node visit (1.2 triangle tests) plus the children's expected tests
+            const double parent_area = box.half_area();
+            const bool split_pays = best_axis >= 0 && (parent_area <= 0 || 1.2 + best / parent_area < double(count));
+            if (count <= kMaxLeaf && !split_pays) return make_leaf(begin, end);
+            if (best_axis >= 0) {
+                const double scale = double(kBins) / ext[best_axis];
+                auto it = std::partition(prims.begin() + begin, prims.begin() + end, [&](const BuildPrim& p) {
+                    int k = int((p.c[best_axis] - cb.lo[best_axis]) * scale);
+                    k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                    return k <= best_bin;
+                });
+                mid = int(it - prims.begin());
             }
-            out.chunk_lo.push_back({plo[0], plo[1], plo[2], R(0)});
-            out.chunk_hi.push_back({phi[0], phi[1], phi[2], R(0)});
-            meta.y++;
+        } else if (count <= kMaxLeaf) {
+            return make_leaf(begin, end);
         }
+        if (mid <= begin || mid >= end) {                 // no usable SAH split: object median along the widest axis
+            int axis = 0;
+            if (ext[1] > ext[axis]) axis = 1;
+            if (ext[2] > ext[axis]) axis = 2;
+            mid = begin + count / 2;
+            std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
+                             [axis](const BuildPrim& x, const BuildPrim& y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.ref.rank < y.ref.rank); });
+        }
+        const int me = int(out.bvh_child.size());
+        out.bvh_a.push_back({}); out.bvh_b.push_back({}); out.bvh_c.push_back({}); out.bvh_child.push_back(make_int2(0, 0));
+        Box3 b0, b1;
+        const int c0 = build(begin, mid, depth + 1, b0);
+        const int c1 = build(mid, end, depth + 1, b1);
+        R l0[3], h0[3], l1[3], h1[3];
+        padded<R>(b0, l0, h0); padded<R>(b1, l1, h1);
+        out.bvh_a[size_t(me)] = {l0[0], h0[0], l0[1], h0[1]};
+        out.bvh_b[size_t(me)] = {l0[2], h0[2], l1[0], h1[0]};
+        out.bvh_c[size_t(me)] = {l1[1], h1[1], l1[2], h1[2]};
+        out.bvh_child[size_t(me)] = make_int2(c0, c1);
+        return me;
     }
-    out.node_meta.push_back(meta);
-    for (int k = 0; k < 2; ++k) {
-        if (s.children[k] <= 0) continue;
-        SubtreeInfo child;
-        emit_subtree(groups, n_groups, tris, n_tris, s.children[k], depth + 1, out, child);
-        info.merge(child);
+};
+
+// One group object: reference nodes, then the rebuilt BVH over all its triangles.
+template <typename R>
+void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int n_groups, const ptw_triangle* tris, int n_tris, HostScene<R>& out,
+                ptk::DMesh<R>& m) {
+    std::vector<RefTri> list;
+    bool nested = true;
+    for (int c = 0; c < s.child_count; ++c) collect_reference_nodes<R>(groups, n_groups, n_tris, s.children[c], -1, 0, out, list, nested);
+    m.flags = nested ? 1 : 0;
+    std::vector<BuildPrim> prims;
+    prims.reserve(list.size());
+    for (const RefTri& r : list) {
+        const ptw_triangle& t = tris[r.src];
+        BuildPrim p;
+        p.ref = r;
+        bool finite = true;
+        double v[3][3];
+        for (int a = 0; a < 3; ++a) {
+            // the vertices the device test actually uses: p1, p1 + e1, p1 + e2 (tracer.cl:640-675 never reads p2 / p3)
+            v[0][a] = t.p1[a]; v[1][a] = t.p1[a] + t.e1[a]; v[2][a] = t.p1[a] + t.e2[a];
+            finite = finite && std::isfinite(v[0][a]) && std::isfinite(v[1][a]) && std::isfinite(v[2][a]);
+        }
+        // A triangle with a NaN / infinite coordinate can never be recorded with EPSILON < t < 1024: every
+        // product of the test that involves it is NaN, +-inf or 0 and fails `t > EPSILON` or the u/v range.
+        if (!finite) continue;
+        for (int k = 0; k < 3; ++k) p.box.add(v[k]);
+        for (int a = 0; a < 3; ++a) p.c[a] = 0.5 * (p.box.lo[a] + p.box.hi[a]);
+        prims.push_back(p);
     }
-    out.node_meta[size_t(me)].z = int(out.node_lo.size());
-    for (int a = 0; a < 3; ++a) {
-        if (info.lo[a] > info.hi[a]) continue;                       // no triangles below this node
-        const double tol = 1e-9 * (1.0 + std::fabs(info.lo[a]) + std::fabs(info.hi[a]));
-        if (!(s.bb_min[a] <= info.lo[a] + tol && s.bb_max[a] >= info.hi[a] - tol)) info.consistent = false;
+    if (prims.empty()) { m.bvh_root = -1; return; }
+    BvhBuilder<R> builder{tris, out, prims};
+    Box3 root_box;
+    int root = builder.build(0, int(prims.size()), 0, root_box);
+    if (root < 0) {                                       // a single leaf: give it a node to hang from
+        const int me = int(out.bvh_child.size());
+        R lo[3], hi[3];
+        padded<R>(root_box, lo, hi);
+        out.bvh_a.push_back({lo[0], hi[0], lo[1], hi[1]});
+        out.bvh_b.push_back({lo[2], hi[2], lo[0], hi[0]});
+        out.bvh_c.push_back({lo[1], hi[1], lo[2], hi[2]});
+        out.bvh_child.push_back(make_int2(root, ~0));     // second child: a leaf of zero triangles
+        root = me;
     }
+    if (builder.max_depth + 2 > ptk::kMeshStack) fail("object %d: rebuilt BVH is %d levels deep (limit %d)", obj_index, builder.max_depth, ptk::kMeshStack - 2);
+    out.mesh_depth = std::max(out.mesh_depth, builder.max_depth);
+    m.bvh_root = root;
+    R lo[3], hi[3];
+    padded<R>(root_box, lo, hi);
+    for (int a = 0; a < 3; ++a) { m.root_lo[a] = lo[a]; m.root_hi[a] = hi[a]; }
 }
 
 template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
@@ -206,37 +303,25 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
             const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
             o.plane_n[0] = R(nx / len); o.plane_n[1] = R(ny / len); o.plane_n[2] = R(nz / len);
         }
-        h.node_begin = h.node_end = int(out.node_lo.size());
+        h.node_begin = h.node_end = 0;
         if (h.type == 2) { h.aux[0] = R(s.min_y); h.aux[1] = R(s.max_y); }
         if (h.type == 1 && s.inverse[1] == 0.0 && s.inverse[2] == 0.0 && s.inverse[4] == 0.0 && s.inverse[6] == 0.0 &&
             s.inverse[8] == 0.0 && s.inverse[9] == 0.0)
             h.type = 5;                                         // intersection-loop fast path; o.type stays 1 for shading
+        ptk::DMesh<R> m;
+        std::memset(&m, 0, sizeof m);
+        m.bvh_root = -1;
         if (h.type == 4) {
-            for (int k = 0; k < 3; ++k) { h.aux[k] = R(s.bb_min[k]); h.aux[3 + k] = R(s.bb_max[k]); }
+            for (int k = 0; k < 3; ++k) { h.aux[k] = R(s.bb_min[k]); h.aux[3 + k] = R(s.bb_max[k]); }   // object AABB, tracer.cl:609
             if (s.child_count > 0) {
                 if (s.child_count > PTW_MAX_ROOT_CHILDREN) fail("object %d: child_count %d > %d", i, s.child_count, PTW_MAX_ROOT_CHILDREN);
                 if (!groups || job.n_groups <= 0) fail("object %d is a group but no BVH groups were passed", i);
-                SubtreeInfo all;
-                for (int c = 0; c < s.child_count; ++c) {
-                    SubtreeInfo child;
-                    emit_subtree<R>(groups, job.n_groups, tris, job.n_triangles, s.children[c], 0, out, child);
-                    all.merge(child);
-                }
+                h.node_begin = int(out.node_lo.size());
+                build_mesh<R>(s, i, groups, job.n_groups, tris, job.n_triangles, out, m);
                 h.node_end = int(out.node_lo.size());
-                if (!all.consistent) h.pad |= 2;                    // some node box does not contain its subtree: no culling
-                const bool unbounded = std::isinf(s.bb_min[0]) && std::isinf(s.bb_min[1]) && std::isinf(s.bb_min[2]) && s.bb_min[0] < 0 &&
-                                       std::isinf(s.bb_max[0]) && std::isinf(s.bb_max[1]) && std::isinf(s.bb_max[2]) && s.bb_max[0] > 0;
-                if (unbounded && all.consistent && all.lo[0] <= all.hi[0]) {
-                    // An all-infinite object box always passes upstream; replace it by the padded extent of the
-                    // triangles as a conservative pre-cull (pad bit 0) so rays far from the mesh skip the root walk.
-                    for (int a = 0; a < 3; ++a) {
-                        const double padv = 1e-4 * (all.hi[a] - all.lo[a]) + 1e-6 * std::max(std::fabs(all.lo[a]), std::fabs(all.hi[a])) + 1e-9;
-                        h.aux[a] = R(all.lo[a] - 2 * padv); h.aux[3 + a] = R(all.hi[a] + 2 * padv);
-                    }
-                    h.pad |= 1;
-                }
             }
         }
+        out.mesh.push_back(m);
         out.shade.push_back(o);
     }
     // runs of consecutive same-type objects (order preserved)
@@ -276,8 +361,10 @@ struct DeviceState {
     std::vector<int> rows;          // frame rows owned by this device, increasing
     std::vector<void*> allocs;      // everything allocated on this device
     cudaMemPool_t pool = nullptr;   // stream-ordered pool (single-GPU contexts), else plain cudaMalloc
-    void* shade = nullptr; void* lens = nullptr; void* node_lo = nullptr; void* node_hi = nullptr; void* node_meta = nullptr;
-    void* tri_test = nullptr; void* tri_shade = nullptr; void* tri_orig = nullptr; void* chunk_lo = nullptr; void* chunk_hi = nullptr;
+    void* shade = nullptr; void* lens = nullptr; void* mesh = nullptr;
+    void* node_lo = nullptr; void* node_hi = nullptr; void* node_parent = nullptr;
+    void* bvh_a = nullptr; void* bvh_b = nullptr; void* bvh_c = nullptr; void* bvh_child = nullptr;
+    void* tri_test = nullptr; void* tri_shade = nullptr; void* tri_info = nullptr;
     void* tex[3] = {nullptr, nullptr, nullptr};
     double* seeds = nullptr;
     int* row_map = nullptr;
@@ -286,6 +373,8 @@ struct DeviceState {
     double* acc = nullptr;          // rows*W*4 running sums of a progressive render
     uchar4* rgba8 = nullptr;        // rows*W tone-mapped bytes (ptc_read_rgba8)
     int slices = 1;
+    int mesh_block = 256;           // threads per block of the mesh kernel (128 or 256)
+    int drain_threshold = 64;       // queued rays that trigger a BVH pass
     int sm_count = 0;
     float last_ms = 0.f;
 };
@@ -357,12 +446,15 @@ template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const Ho
     d.lens = s.lens.empty() ? nullptr : upload(d, s.lens, h2d);
     d.node_lo = upload(d, s.node_lo, h2d);
     d.node_hi = upload(d, s.node_hi, h2d);
-    d.node_meta = upload(d, s.node_meta, h2d);
+    d.node_parent = upload(d, s.node_parent, h2d);
+    d.mesh = upload(d, s.mesh, h2d);
+    d.bvh_a = upload(d, s.bvh_a, h2d);
+    d.bvh_b = upload(d, s.bvh_b, h2d);
+    d.bvh_c = upload(d, s.bvh_c, h2d);
+    d.bvh_child = upload(d, s.bvh_child, h2d);
     d.tri_test = upload(d, s.tri_test, h2d);
     d.tri_shade = upload(d, s.tri_shade, h2d);
-    d.tri_orig = upload(d, s.tri_orig, h2d);
-    d.chunk_lo = upload(d, s.chunk_lo, h2d);
-    d.chunk_hi = upload(d, s.chunk_hi, h2d);
+    d.tri_info = upload(d, s.tri_info, h2d);
     (void)c;
 }
 
@@ -377,12 +469,15 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     P.n_objects = c.n_objects;
     P.node_lo = static_cast<const ptk::V4<R>*>(d.node_lo);
     P.node_hi = static_cast<const ptk::V4<R>*>(d.node_hi);
-    P.node_meta = static_cast<const int4*>(d.node_meta);
+    P.node_parent = static_cast<const int*>(d.node_parent);
+    P.mesh = static_cast<const ptk::DMesh<R>*>(d.mesh);
+    P.bvh_a = static_cast<const ptk::V4<R>*>(d.bvh_a);
+    P.bvh_b = static_cast<const ptk::V4<R>*>(d.bvh_b);
+    P.bvh_c = static_cast<const ptk::V4<R>*>(d.bvh_c);
+    P.bvh_child = static_cast<const int2*>(d.bvh_child);
     P.tri_test = static_cast<const ptk::V4<R>*>(d.tri_test);
     P.tri_shade = static_cast<const ptk::V4<R>*>(d.tri_shade);
-    P.tri_orig = static_cast<const int*>(d.tri_orig);
-    P.chunk_lo = static_cast<const ptk::V4<R>*>(d.chunk_lo);
-    P.chunk_hi = static_cast<const ptk::V4<R>*>(d.chunk_hi);
+    P.tri_info = static_cast<const int2*>(d.tri_info);
     P.cam = s.cam;
     for (int k = 0; k < 3; ++k) P.tex[k] = ptk::DTex{static_cast<const uchar4*>(d.tex[k]), c.tex_w[k], c.tex_h[k], c.tex_layers[k]};
     P.seeds = d.seeds;
@@ -417,18 +512,31 @@ template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScen
     const int tiles_x = (c.width + ptk::kTileW - 1) / ptk::kTileW;
     const int tiles_y = (rows + ptk::kTileH - 1) / ptk::kTileH;
     const long long warps = (long long)tiles_x * tiles_y;
-    const int warps_per_block = ptk::kBlockThreads / 32;
-    dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
-    dim3 block(ptk::kBlockThreads, 1, 1);
-    bool groups = false;
-    for (int i = 0; i < c.n_objects; ++i) groups = groups || (s.hot[i].type == 4 && s.hot[i].node_end > s.hot[i].node_begin);
+    bool meshes = false;
+    for (int i = 0; i < c.n_objects; ++i) meshes = meshes || s.mesh[size_t(i)].bvh_root >= 0;
     const bool fast = c.rng_mode == PTC_RNG_FAST;
-    if (groups) {
-        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, true><<<grid, block, 0, d.stream>>>(P);
-        else ptk::trace_kernel<R, ptk::RNG_PARITY, true><<<grid, block, 0, d.stream>>>(P);
+    if (meshes) {
+        // scenes with meshes: block-wide ray queue, see trace_mesh_kernel
+        int threads = d.mesh_block;
+        P.drain_threshold = d.drain_threshold;
+        const int warps_per_block = threads / 32;
+        dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
+        const size_t smem = ptk::MeshShared<R>::bytes(threads);
+        auto go = [&](auto kernel) {
+            CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            kernel<<<grid, dim3((unsigned)threads, 1, 1), smem, d.stream>>>(P);
+        };
+        if (threads == 256) {
+            if (fast) go(ptk::trace_mesh_kernel<R, ptk::RNG_FAST, 256>); else go(ptk::trace_mesh_kernel<R, ptk::RNG_PARITY, 256>);
+        } else {
+            if (fast) go(ptk::trace_mesh_kernel<R, ptk::RNG_FAST, 128>); else go(ptk::trace_mesh_kernel<R, ptk::RNG_PARITY, 128>);
+        }
     } else {
-        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, false><<<grid, block, 0, d.stream>>>(P);
-        else ptk::trace_kernel<R, ptk::RNG_PARITY, false><<<grid, block, 0, d.stream>>>(P);
+        const int warps_per_block = ptk::kBlockThreads / 32;
+        dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
+        dim3 block(ptk::kBlockThreads, 1, 1);
+        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST><<<grid, block, 0, d.stream>>>(P);
+        else ptk::trace_kernel<R, ptk::RNG_PARITY><<<grid, block, 0, d.stream>>>(P);
     }
     CUDA_OK(cudaGetLastError());
     c.stats.kernel_launches++;
@@ -567,6 +675,8 @@ ptc_context* open_impl(const ptc_job& job) {
         if (sl > 32) sl = 32;
         if (sl < 1) sl = 1;
         d.slices = int(sl);
+        if (const char* ov = std::getenv("PTC_MESH_BLOCK")) d.mesh_block = std::atoi(ov) == 128 ? 128 : 256;   // tuning overrides
+        if (const char* ov = std::getenv("PTC_MESH_DRAIN")) d.drain_threshold = std::max(1, std::atoi(ov));
     }
     if (nd > 1) {
         DeviceState& d0 = c.dev[0];
@@ -881,6 +991,48 @@ int ptc_debug_noise3d(const float* xyz, int n, int rng_mode, float* out, char* e
         cudaFree(dx); cudaFree(dout);
         CUDA_OK(e);
     });
+}
+
+// Test hook (not part of the drop-in surface; host only, no device needed): flattens the job's scene in
+// double and copies one array of the rebuilt mesh index out, so tests can check the builder's invariants
+// (every triangle in exactly one leaf, child boxes containing their triangles, depth) and replay the walk.
+// what: 0 bvh_a, 1 bvh_b, 2 bvh_c, 3 bvh_child, 4 tri_info, 5 tri_test, 6 node_lo, 7 node_hi, 8 node_parent,
+// 9 mesh records (8 doubles per object: root_lo, root_hi, bvh_root, flags), 10 object node ranges (2 ints per object).
+// Returns the array's size in bytes (copying at most cap_bytes), or -1 with a message.
+int64_t ptc_debug_mesh_index(const ptc_job* job, int what, void* out, int64_t cap_bytes, char* err, int errlen) {
+    int64_t bytes = -1;
+    int rc = guarded(err, errlen, [&] {
+        if (!job) fail("job is NULL");
+        validate(*job);
+        HostScene<double> hs;
+        flatten<double>(*job, hs);
+        std::vector<double> mesh;
+        std::vector<int> ranges;
+        for (int i = 0; i < job->n_objects; ++i) {
+            const ptk::DMesh<double>& m = hs.mesh[size_t(i)];
+            for (int a = 0; a < 3; ++a) mesh.push_back(m.root_lo[a]);
+            for (int a = 0; a < 3; ++a) mesh.push_back(m.root_hi[a]);
+            mesh.push_back(double(m.bvh_root)); mesh.push_back(double(m.flags));
+            ranges.push_back(hs.hot[i].node_begin); ranges.push_back(hs.hot[i].node_end);
+        }
+        const void* src = nullptr;
+        switch (what) {
+            case 0: src = hs.bvh_a.data(); bytes = int64_t(hs.bvh_a.size() * sizeof(hs.bvh_a[0])); break;
+            case 1: src = hs.bvh_b.data(); bytes = int64_t(hs.bvh_b.size() * sizeof(hs.bvh_b[0])); break;
+            case 2: src = hs.bvh_c.data(); bytes = int64_t(hs.bvh_c.size() * sizeof(hs.bvh_c[0])); break;
+            case 3: src = hs.bvh_child.data(); bytes = int64_t(hs.bvh_child.size() * sizeof(int2)); break;
+            case 4: src = hs.tri_info.data(); bytes = int64_t(hs.tri_info.size() * sizeof(int2)); break;
+            case 5: src = hs.tri_test.data(); bytes = int64_t(hs.tri_test.size() * sizeof(hs.tri_test[0])); break;
+            case 6: src = hs.node_lo.data(); bytes = int64_t(hs.node_lo.size() * sizeof(hs.node_lo[0])); break;
+            case 7: src = hs.node_hi.data(); bytes = int64_t(hs.node_hi.size() * sizeof(hs.node_hi[0])); break;
+            case 8: src = hs.node_parent.data(); bytes = int64_t(hs.node_parent.size() * sizeof(int)); break;
+            case 9: src = mesh.data(); bytes = int64_t(mesh.size() * sizeof(double)); break;
+            case 10: src = ranges.data(); bytes = int64_t(ranges.size() * sizeof(int)); break;
+            default: fail("ptc_debug_mesh_index: unknown array %d", what);
+        }
+        if (out && cap_bytes > 0 && bytes > 0) std::memcpy(out, src, size_t(std::min(bytes, cap_bytes)));
+    });
+    return rc == 0 ? bytes : -1;
 }
 
 }  // extern "C"

@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
         L.ptc_trace_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int]
         L.ptc_reset.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.ptc_read_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_debug_mesh_index.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_char_p, C.c_int]
+        L.ptc_debug_mesh_index.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -314,4 +316,31 @@ def debug_noise3d(xyz: np.ndarray, rng_mode: int = RNG_PARITY) -> np.ndarray:
     err = C.create_string_buffer(512)
     if lib().ptc_debug_noise3d(a.ctypes.data, a.shape[0], rng_mode, out.ctypes.data, err, 512) != 0:
         raise PtcError(err.value.decode())
+    return out
+
+
+_MESH_INDEX_ARRAYS = {  # name -> (selector, dtype, trailing shape)
+    "bvh_a": (0, np.float64, (4,)), "bvh_b": (1, np.float64, (4,)), "bvh_c": (2, np.float64, (4,)),
+    "bvh_child": (3, np.int32, (2,)), "tri_info": (4, np.int32, (2,)), "tri_test": (5, np.float64, (3, 4)),
+    "node_lo": (6, np.float64, (4,)), "node_hi": (7, np.float64, (4,)), "node_parent": (8, np.int32, ()),
+    "mesh": (9, np.float64, (8,)), "node_range": (10, np.int32, (2,)),
+}
+
+
+def debug_mesh_index(scene) -> dict:
+    """Test hook (host only, no device needed): the rebuilt mesh BVH and the reference-node tables the C
+    layer derives from a scene's triangles/groups, in double, as numpy arrays."""
+    seeds = np.zeros(scene.width * scene.height)
+    job = _Job(scene.objects, scene.triangles if scene.n_triangles else None, scene.groups if scene.n_groups else None,
+               scene.camera, None, None, None, seeds, 1, FP64, RNG_PARITY, None, 0, 1, 0)
+    out = {}
+    for name, (sel, dtype, tail) in _MESH_INDEX_ARRAYS.items():
+        err = C.create_string_buffer(512)
+        n = lib().ptc_debug_mesh_index(C.byref(job.struct), sel, None, 0, err, 512)
+        if n < 0:
+            raise PtcError(err.value.decode())
+        buf = np.zeros(max(n, 1), dtype=np.uint8)
+        if n > 0 and lib().ptc_debug_mesh_index(C.byref(job.struct), sel, buf.ctypes.data, n, err, 512) < 0:
+            raise PtcError(err.value.decode())
+        out[name] = buf[:n].view(dtype).reshape((-1,) + tail)
     return out

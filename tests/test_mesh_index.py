@@ -1,0 +1,304 @@
+"""The rebuilt mesh BVH (pathtracer_ocl_b200/csrc/ptcuda.cu: BvhBuilder) is only an INDEX: which triangle wins
+must still be what the reference's own walk (tracer.cl:598-742) would have picked.  These CPU tests use the
+host-only hook `ptc_debug_mesh_index` (no device, no compute) to
+  * check the invariants the exactness argument needs from the builder: every triangle in exactly one leaf,
+    every stored child box a superset of the triangles below it, depth within the device stack;
+  * replay the device walk (trace.cuh: mesh_walk) in numpy, in double, and compare its winner with a
+    brute-force statement of the reference rule on the same rays -- including rays with zero direction
+    components (|d| < EPSILON -> HUGE_VAL slabs), rays starting inside the mesh and rays grazing flat boxes.
+The CUDA code itself is tested against the oracle in tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from pathtracer_ocl_b200 import scene as S, trace as T
+
+EPS = 1e-4
+MESH_STACK = 40            # trace.cuh: kMeshStack
+SLACK = 1e-13              # trace.cuh: box_slack<double>()
+
+
+def index_of(scene):
+    m = T.debug_mesh_index(scene)
+    obj = int(np.flatnonzero(m["mesh"][:, 6] >= 0)[0])
+    return m, obj
+
+
+def leaf_slots(code):
+    c = ~int(code)
+    return c >> 3, c & 7
+
+
+def subtree(m, child, depth, seen, depth_max):
+    """Returns (lo, hi) of the triangle vertices below `child`; checks stored boxes on the way."""
+    depth_max[0] = max(depth_max[0], depth)
+    if child < 0:
+        first, count = leaf_slots(child)
+        assert count <= 4
+        lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+        for n in range(first, first + count):
+            assert not seen[n]
+            seen[n] = True
+            q = m["tri_test"][n]
+            p1 = q[0, :3]
+            e1 = np.array([q[0, 3], q[1, 0], q[1, 1]])
+            e2 = np.array([q[1, 2], q[1, 3], q[2, 0]])
+            for v in (p1, p1 + e1, p1 + e2):
+                lo, hi = np.minimum(lo, v), np.maximum(hi, v)
+        return lo, hi
+    a, b, c = m["bvh_a"][child], m["bvh_b"][child], m["bvh_c"][child]
+    boxes = ((np.array([a[0], a[2], b[0]]), np.array([a[1], a[3], b[1]])), (np.array([b[2], c[0], c[2]]), np.array([b[3], c[1], c[3]])))
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for k in range(2):
+        clo, chi = subtree(m, int(m["bvh_child"][child, k]), depth + 1, seen, depth_max)
+        if np.isfinite(clo).all():
+            assert (boxes[k][0] < clo).all() and (boxes[k][1] > chi).all(), "stored child box must strictly contain its triangles"
+        lo, hi = np.minimum(lo, clo), np.maximum(hi, chi)
+    return lo, hi
+
+
+@pytest.mark.parametrize("name", ["teapot", "gopher"])
+def test_builder_invariants(name):
+    sc = S.build_scene(name, 32, 24)
+    m, obj = index_of(sc)
+    n = m["tri_info"].shape[0]
+    assert n == sc.n_triangles
+    assert sorted(m["tri_info"][:, 0].tolist()) == list(range(n)), "ranks are a permutation of the recording order"
+    seen = np.zeros(n, dtype=bool)
+    depth_max = [0]
+    lo, hi = subtree(m, int(m["mesh"][obj, 6]), 0, seen, depth_max)
+    assert seen.all(), "every triangle sits in exactly one leaf"
+    assert depth_max[0] + 2 <= MESH_STACK
+    assert (m["mesh"][obj, 0:3] < lo).all() and (m["mesh"][obj, 3:6] > hi).all()
+    # reference nodes: parents precede children (pre-order), triangles point at existing nodes
+    par = m["node_parent"]
+    assert (par < np.arange(par.size)).all() and (par >= -1).all()
+    assert m["tri_info"][:, 1].min() >= 0 and m["tri_info"][:, 1].max() < par.size
+    # the reference's recording order: rank increases with the (pre-order) node index
+    order = np.argsort(m["tri_info"][:, 0])
+    assert (np.diff(m["tri_info"][order, 1]) >= 0).all()
+
+
+# ---- the reference rule, brute force ---------------------------------------------------------------
+def ref_box(o, d, lo, hi):
+    """tracer.cl:250-280 for many boxes at once (lo, hi: [n,3]); returns bool[n]."""
+    with np.errstate(all="ignore"):
+        big = np.abs(d) >= EPS
+        a, b = lo - o, hi - o
+        t0 = np.where(big, a / np.where(big, d, 1.0), a * np.inf)
+        t1 = np.where(big, b / np.where(big, d, 1.0), b * np.inf)
+        sw = t0 > t1
+        tn, tf = np.where(sw, t1, t0), np.where(sw, t0, t1)
+        tmin = np.fmax(np.fmax(tn[:, 0], tn[:, 1]), tn[:, 2])
+        tmax = np.fmin(np.fmin(tf[:, 0], tf[:, 1]), tf[:, 2])
+        return tmin < tmax
+
+
+def moller_trumbore(o, d, tt):
+    """tracer.cl:640-675 for many triangles; returns (ok, t, u, v)."""
+    with np.errstate(all="ignore"):
+        p1 = tt[:, 0, :3]
+        e1 = np.stack([tt[:, 0, 3], tt[:, 1, 0], tt[:, 1, 1]], axis=1)
+        e2 = np.stack([tt[:, 1, 2], tt[:, 1, 3], tt[:, 2, 0]], axis=1)
+        dxe2 = np.cross(d[None, :], e2)
+        det = e1[:, 0] * dxe2[:, 0] + e1[:, 1] * dxe2[:, 1] + e1[:, 2] * dxe2[:, 2]
+        f = 1.0 / det
+        sv = o[None, :] - p1
+        u = f * (sv[:, 0] * dxe2[:, 0] + sv[:, 1] * dxe2[:, 1] + sv[:, 2] * dxe2[:, 2])
+        sxe1 = np.cross(sv, e1)
+        v = f * (d[0] * sxe1[:, 0] + d[1] * sxe1[:, 1] + d[2] * sxe1[:, 2])
+        t = f * (e2[:, 0] * sxe1[:, 0] + e2[:, 1] * sxe1[:, 1] + e2[:, 2] * sxe1[:, 2])
+        ok = ~(np.abs(det) < EPS) & ~((u < 0) | (u > 1)) & ~((v < 0) | ((u + v) > 1))
+        return ok, t, u, v
+
+
+def reference_winner(m, obj_lo, obj_hi, o, d, best_t):
+    """Slot of the triangle the reference records as closest with EPS < t < best_t (ties: first recorded), or -1."""
+    if not np.isfinite(o).all() or not np.isfinite(d).all():
+        return -1, best_t
+    if not ref_box(o, d, obj_lo[None, :], obj_hi[None, :])[0]:
+        return -1, best_t
+    hit = ref_box(o, d, m["node_lo"][:, :3], m["node_hi"][:, :3])
+    tested = np.zeros(hit.size, dtype=bool)
+    par = m["node_parent"]
+    for g in range(hit.size):                       # pre-order: a parent is settled before its children
+        tested[g] = hit[g] and (par[g] < 0 or tested[par[g]])
+    ok, t, _, _ = moller_trumbore(o, d, m["tri_test"])
+    cand = ok & tested[m["tri_info"][:, 1]] & (t > EPS) & (t < best_t)
+    if not cand.any():
+        return -1, best_t
+    idx = np.flatnonzero(cand)
+    tmin = t[idx].min()
+    tie = idx[t[idx] == tmin]
+    return int(tie[np.argmin(m["tri_info"][tie, 0])]), float(tmin)
+
+
+# ---- the device walk, replayed ------------------------------------------------------------------------
+def keep_box(o, k, lo, hi, limit):
+    with np.errstate(all="ignore"):
+        t0, t1 = (lo - o) * k, (hi - o) * k
+        tn = np.fmax(np.fmax(np.fmin(t0[0], t1[0]), np.fmin(t0[1], t1[1])), np.fmax(np.fmin(t0[2], t1[2]), 0.0))
+        tf = np.fmin(np.fmin(np.fmax(t0[0], t1[0]), np.fmax(t0[1], t1[1])), np.fmin(np.fmax(t0[2], t1[2]), limit))
+        return (not (tn > tf + tf * SLACK)), tn
+
+
+def chain_ok(m, o, d, g, whole_chain):
+    while g >= 0:
+        if not ref_box(o, d, m["node_lo"][g:g + 1, :3], m["node_hi"][g:g + 1, :3])[0]:
+            return False
+        g = int(m["node_parent"][g]) if whole_chain else -1
+    return True
+
+
+def replayed_winner(m, mesh_row, obj_lo, obj_hi, o, d, best_t, stats):
+    if not np.isfinite(o).all() or not np.isfinite(d).all():
+        return -1, best_t
+    if not ref_box(o, d, obj_lo[None, :], obj_hi[None, :])[0]:
+        return -1, best_t
+    with np.errstate(all="ignore"):
+        k = 1.0 / d
+    keep, _ = keep_box(o, k, mesh_row[0:3], mesh_row[3:6], best_t * 1.0001)
+    if not keep:
+        return -1, best_t
+    nested = int(mesh_row[7]) & 1
+    whole_chain = (not nested) or not (np.abs(d) >= EPS).all()
+    ct, crank, cslot = best_t, -1, -1
+    node, stack = int(mesh_row[6]), []
+    while True:
+        if node >= 0:
+            stats["nodes"] += 1
+            a, b, c = m["bvh_a"][node], m["bvh_b"][node], m["bvh_c"][node]
+            ch = m["bvh_child"][node]
+            lim = ct * 1.0001
+            h0, tn0 = keep_box(o, k, np.array([a[0], a[2], b[0]]), np.array([a[1], a[3], b[1]]), lim)
+            h1, tn1 = keep_box(o, k, np.array([b[2], c[0], c[2]]), np.array([b[3], c[1], c[3]]), lim)
+            if h0 and h1:
+                swap = tn1 < tn0
+                stack.append(int(ch[0] if swap else ch[1]))
+                assert len(stack) <= MESH_STACK
+                node = int(ch[1] if swap else ch[0])
+                continue
+            if h0 or h1:
+                node = int(ch[0] if h0 else ch[1])
+                continue
+        else:
+            first, count = leaf_slots(node)
+            if count:
+                stats["tris"] += count
+                ok, t, _, _ = moller_trumbore(o, d, m["tri_test"][first:first + count])
+                for q in range(count):
+                    n = first + q
+                    if ok[q] and t[q] > EPS and t[q] <= ct:
+                        rank, ref = m["tri_info"][n]
+                        if (t[q] < ct or rank < crank) and chain_ok(m, o, d, int(ref), whole_chain):
+                            ct, crank, cslot = float(t[q]), int(rank), n
+        if not stack:
+            break
+        node = stack.pop()
+    return cslot, ct
+
+
+def rays_for(m, obj_lo, obj_hi, rng, n):
+    """Object-space rays: random ones aimed at the mesh, axis-parallel ones, ones starting inside, ones aimed at vertices."""
+    lo, hi = m["mesh"][:, 0:3][m["mesh"][:, 6] >= 0][0], m["mesh"][:, 3:6][m["mesh"][:, 6] >= 0][0]
+    c, ext = 0.5 * (lo + hi), (hi - lo)
+    rays = []
+    for i in range(n):
+        kind = i % 6
+        target = c + (rng.random(3) - 0.5) * ext
+        if kind == 0:                                   # from outside towards the mesh
+            o = c + rng.normal(size=3) * ext * 2.5
+            d = target - o
+            d /= np.linalg.norm(d) * rng.uniform(0.05, 20.0)          # object-space directions are not unit length
+        elif kind == 1:                                 # starting inside the extent, any direction
+            o = target
+            d = rng.normal(size=3)
+        elif kind == 2:                                 # one direction component exactly zero (HUGE_VAL slab)
+            o = c + rng.normal(size=3) * ext * 1.5
+            d = target - o
+            a = rng.integers(3)
+            d[a] = 0.0
+            o[a] = target[a]
+        elif kind == 3:                                 # one component below EPSILON but not zero
+            o = c + rng.normal(size=3) * ext * 1.5
+            d = target - o
+            a = rng.integers(3)
+            d[a] = rng.uniform(-0.9e-4, 0.9e-4)
+            o[a] = target[a] + rng.uniform(-0.01, 0.01)
+        elif kind == 4:                                 # aimed exactly at a triangle vertex (box corners / edges)
+            q = m["tri_test"][rng.integers(m["tri_test"].shape[0])]
+            o = c + rng.normal(size=3) * ext * 2.0
+            d = q[0, :3] - o
+        else:                                           # along an axis through the mesh
+            a = rng.integers(3)
+            o = target.copy()
+            o[a] = lo[a] - 1.0
+            d = np.zeros(3)
+            d[a] = rng.uniform(0.5, 3.0)
+        rays.append((o, d))
+    return rays
+
+
+@pytest.mark.parametrize("name,n_rays", [("teapot", 700), ("gopher", 400)])
+def test_replayed_walk_picks_the_reference_winner(name, n_rays):
+    sc = S.build_scene(name, 32, 24)
+    m, obj = index_of(sc)
+    ob = sc.objects_view()[obj]
+    obj_lo, obj_hi = np.array(ob["bb_min"][:3]), np.array(ob["bb_max"][:3])
+    rng = np.random.default_rng(7)
+    stats = {"nodes": 0, "tris": 0}
+    hits = 0
+    for i, (o, d) in enumerate(rays_for(m, obj_lo, obj_hi, rng, n_rays)):
+        best_t = 1024.0 if i % 3 else float(rng.uniform(0.5, 30.0))      # sometimes an analytic hit limits the search
+        want = reference_winner(m, obj_lo, obj_hi, o, d, best_t)
+        got = replayed_winner(m, m["mesh"][obj], obj_lo, obj_hi, o, d, best_t, stats)
+        assert got == want, f"ray {i}: replay {got} vs reference {want} (o={o}, d={d})"
+        hits += want[0] >= 0
+    assert hits > n_rays // 4
+    print(f"{name}: {hits}/{n_rays} rays hit; {stats['nodes'] / n_rays:.1f} nodes and {stats['tris'] / n_rays:.1f} triangle tests per ray "
+          f"(the reference walk tests every triangle of every node it enters)")
+
+
+def flat_box_scene():
+    """A mesh whose BVH has a node with a FLAT box (an axis-aligned quad): the reference's strict tmin < tmax never
+    passes such a box, so its triangles are invisible upstream -- and must be here."""
+    obj = """
+v -1 0 -1
+v 1 0 -1
+v 1 0 1
+v -1 0 1
+v -1 0.5 -1
+v 1 0.9 -1
+v 1 1.3 1
+v -1 0.7 1
+g flat
+f 1 2 3 4
+g tilted
+f 5 6 7 8
+"""
+    return S.scene_from_obj(obj, divide_threshold=1)[0]
+
+
+def test_flat_reference_boxes_hide_their_triangles():
+    sc = flat_box_scene()
+    m, obj = index_of(sc)
+    ob = sc.objects_view()[obj]
+    obj_lo, obj_hi = np.array(ob["bb_min"][:3]), np.array(ob["bb_max"][:3])
+    flat = np.flatnonzero((m["node_lo"][:, :3] == m["node_hi"][:, :3]).any(axis=1))
+    assert flat.size > 0, "the scene is meant to contain a flat node box"
+    rng = np.random.default_rng(3)
+    stats = {"nodes": 0, "tris": 0}
+    seen_hidden = 0
+    for i in range(300):
+        o = np.array([rng.uniform(-0.9, 0.9), rng.uniform(1.5, 3.0), rng.uniform(-0.9, 0.9)])
+        tgt = np.array([rng.uniform(-0.9, 0.9), 0.0, rng.uniform(-0.9, 0.9)])
+        d = (tgt - o) * rng.uniform(0.2, 2.0)
+        want = reference_winner(m, obj_lo, obj_hi, o, d, 1024.0)
+        got = replayed_winner(m, m["mesh"][obj], obj_lo, obj_hi, o, d, 1024.0, stats)
+        assert got == want
+        ok, t, _, _ = moller_trumbore(o, d, m["tri_test"])
+        under_flat = np.isin(m["tri_info"][:, 1], flat)
+        if (ok & under_flat & (t > EPS)).any():
+            seen_hidden += 1
+            assert want[0] < 0 or not under_flat[want[0]]
+    assert seen_hidden > 100
