@@ -155,7 +155,10 @@ template <typename R> struct alignas(16) DMesh {
     int flags;                  // bit0: every reference node box contains its child boxes (checked on the host in R)
 };
 
-constexpr int kMeshStack = 40;  // deferred-child stack entries per walking thread (host refuses deeper trees)
+constexpr int kWide = 8;                       // children per node = lanes per ray in the cooperative walk
+constexpr int kLeafTris = 8;                   // triangles per leaf (one per lane)
+constexpr int kWideStack = 64;                 // deferred-child stack entries per ray (the host refuses trees that need more)
+constexpr int kEmptyChild = (int)0x80000000;
 
 template <typename R> struct Params {
     DObjHot<R> hot[kMaxObjects];
@@ -166,11 +169,10 @@ template <typename R> struct Params {
     const V4<R>* node_lo;       // (min.xyz, -)
     const V4<R>* node_hi;       // (max.xyz, -)
     const int* node_parent;     // -1 for a root child
-    // rebuilt BVH: binary, SAH, triangles in leaves only; a node holds the padded boxes of its two children
-    const V4<R>* bvh_a;         // (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
-    const V4<R>* bvh_b;         // (c0.lo.z, c0.hi.z, c1.lo.x, c1.hi.x)
-    const V4<R>* bvh_c;         // (c1.lo.y, c1.hi.y, c1.lo.z, c1.hi.z)
-    const int2* bvh_child;      // >= 0: inner node; < 0: leaf, ~code = (first slot << 3) | triangle count
+    // rebuilt BVH: 8-wide, SAH, triangles in leaves only.  Node n, child c: wide[(n*8+c)*2] = (lo.xyz, child code),
+    // wide[(n*8+c)*2+1] = (hi.xyz, -): padded box of the child.  Code >= 0: inner node; kEmptyChild: no child;
+    // otherwise a leaf, ~code = (first slot << 4) | triangle count (<= 8).
+    const V4<R>* wide;
     const DMesh<R>* mesh;       // per object (valid for groups)
     const int2* tri_info;       // per slot: (rank in the reference's recording order, reference node)
     const V4<R>* tri_test;      // 3 per slot: (p1.xyz,e1.x) (e1.yz,e2.xy) (e2.z,-,-,-)
@@ -186,7 +188,6 @@ template <typename R> struct Params {
     int sample_begin, sample_end;   // samples rendered by this launch: [begin, end) (0, samples for a full render)
     int raw_sums;               // 1: write unweighted sums per slice even when slices == 1 (progressive accumulation)
     int slices;                 // sample slices per pixel (gridDim.y)
-    int drain_threshold;        // mesh kernel: queued rays that trigger a block-wide BVH pass
     R pi;                       // (double)3.14159265359f, tracer.cl:1
     R eps;                      // 0.0001, tracer.cl:4
 };
@@ -371,8 +372,9 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // frontend's BVH keeps straddling triangles in inner nodes (46 % of the teapot's), so that walk tests
 // hundreds of triangles per ray.
 //
-// Here the triangles of a group object are re-indexed by a binary SAH BVH with leaves of <= 4 triangles,
-// built by the host layer over the SAME triangle records.  Two facts make the result the reference's:
+// Here the triangles of a group object are re-indexed by an 8-wide SAH BVH with leaves of <= 8
+// triangles, built by the host layer over the SAME triangle records.  Two facts make the result the
+// reference's:
 //   (1) the rebuilt tree only ever culls: its boxes are padded supersets of their triangles and the
 //       slab test keeps a box on any doubt (relative slack, NaN keeps), so every triangle whose
 //       Moeller-Trumbore test could pass with EPSILON < t <= best-so-far is tested, with the reference's
@@ -385,12 +387,25 @@ constexpr unsigned kFullMask = 0xffffffffu;
 //       under rounding -- so testing the triangle's own node box decides the whole chain; otherwise the
 //       chain is walked through the parent links.
 // Ties between equal t go to the lower rank (= position in the reference's recording order).
+//
+// Execution: only a few lanes of a warp have a ray that reaches a mesh on a given segment (ncu on the
+// teapot scene: ~4 of 32), so a per-lane walk idles most of the warp (measured: 7 of 32 lanes active,
+// profiles/r01_v8a_*).  Instead EIGHT LANES SHARE ONE RAY -- a warp walks up to four rays at a time:
+// at an inner node lane c tests the box of child c; at a leaf lane c tests triangle c; the nearest child
+// / closest candidate of a group is found with three shuffle-min steps; the other hit children go to a
+// small per-ray stack in shared memory.  A walk is a handful of dependent steps instead of dozens, and
+// the four groups of a warp run in lockstep, so all shuffles and ballots are warp-convergent.
 template <typename R> struct IDir { R x, y, z; };
 __device__ __forceinline__ IDir<float> inv_dir(V3<float> d) { return {m_rcp(d.x), m_rcp(d.y), m_rcp(d.z)}; }
 __device__ __forceinline__ IDir<double> inv_dir(V3<double> d) { return {1.0 / d.x, 1.0 / d.y, 1.0 / d.z}; }
 template <typename R> __device__ __forceinline__ R box_slack();
 template <> __device__ __forceinline__ float box_slack<float>() { return 8e-6f; }
 template <> __device__ __forceinline__ double box_slack<double>() { return 1e-13; }
+__device__ __forceinline__ int child_code(float w) { return __float_as_int(w); }
+__device__ __forceinline__ int child_code(double w) { return (int)w; }
+// distance bound kept with a stacked child: a float that is <= the true value
+__device__ __forceinline__ int stack_key(float tn) { return __float_as_int(tn); }
+__device__ __forceinline__ int stack_key(double tn) { return __float_as_int(__double2float_rd(tn)); }
 
 // Conservative slab interval of a padded box: [tn, tf] clipped to [0, limit]; "keep" unless provably empty.
 // fmin/fmax drop a NaN operand (0 * inf on an axis the ray is parallel to), which only widens the interval.
@@ -416,11 +431,146 @@ __device__ __forceinline__ bool reference_tests_node(const Params<R>& P, V3<R> o
     return true;
 }
 
-// Does any mesh object need its BVH walked for this ray?  (object AABB under the reference rule AND the
-// padded extent of its triangles within reach of the closest hit so far)
+template <typename R> __device__ __forceinline__ V3<R> shfl3(V3<R> v, int src) {
+    return {__shfl_sync(kFullMask, v.x, src), __shfl_sync(kFullMask, v.y, src), __shfl_sync(kFullMask, v.z, src)};
+}
+// min over the 8 lanes of a group (xor offsets stay inside the group)
+__device__ __forceinline__ float group_min(float v) {
+    v = fminf(v, __shfl_xor_sync(kFullMask, v, 1)); v = fminf(v, __shfl_xor_sync(kFullMask, v, 2)); return fminf(v, __shfl_xor_sync(kFullMask, v, 4));
+}
+__device__ __forceinline__ double group_min(double v) {
+    v = fmin(v, __shfl_xor_sync(kFullMask, v, 1)); v = fmin(v, __shfl_xor_sync(kFullMask, v, 2)); return fmin(v, __shfl_xor_sync(kFullMask, v, 4));
+}
+__device__ __forceinline__ int group_min(int v) {
+    v = min(v, __shfl_xor_sync(kFullMask, v, 1)); v = min(v, __shfl_xor_sync(kFullMask, v, 2)); return min(v, __shfl_xor_sync(kFullMask, v, 4));
+}
+
+// One mesh object against the rays of the lanes with `want` set.  Called by all 32 lanes.  `po`, `pd`:
+// this lane's ray in the object's space.  `stk`: this lane's GROUP's stack in shared memory.
 template <typename R>
-__device__ __forceinline__ bool mesh_wanted(const Params<R>& P, V3<R> ro, V3<R> rd, R best_t) {
-    bool want = false;
+__device__ __forceinline__ void mesh_hit(const Params<R>& P, const DMesh<R>& m, int j, V3<R> po, V3<R> pd, bool want, int lane, Hit<R>& h, int2* __restrict__ stk) {
+    const R eps = P.eps;
+    const int sub = lane & 7, gbase = lane & 24, grp = lane >> 3;
+    constexpr int kDone = 0x7fffffff;
+    unsigned todo = __ballot_sync(kFullMask, want);
+    while (todo) {                                                    // a round: up to four rays, one per group
+        // owners of this round: the four lowest set bits of `todo`
+        const unsigned t1 = todo & (todo - 1), t2 = t1 & (t1 - 1), t3 = t2 & (t2 - 1);
+        const unsigned mine_bits = grp == 0 ? todo : grp == 1 ? t1 : grp == 2 ? t2 : t3;
+        const bool active = mine_bits != 0u;
+        const int owner = active ? __ffs(mine_bits) - 1 : lane;
+        const unsigned round_bits = todo ^ (t3 & (t3 - 1));
+        todo = t3 & (t3 - 1);
+        const V3<R> o = shfl3(po, owner), d = shfl3(pd, owner);
+        R ct = __shfl_sync(kFullMask, h.t, owner);
+        const int cobj = __shfl_sync(kFullMask, h.obj, owner);
+        const IDir<R> k = inv_dir(d);
+        const Slab<R> s = make_slab(d, eps);
+        const bool whole_chain = !(m.flags & 1) || !(s.dx && s.dy && s.dz);
+        int crank = cobj > j ? 0x7fffffff : -1;       // equal t: an earlier object keeps the hit, a later one loses it to this mesh
+        int cslot = -1;
+        R cu = R(0), cv = R(0);
+        int cur = active ? m.bvh_root : kDone, sp = 0;
+
+        while (__any_sync(kFullMask, cur != kDone)) {
+            const bool inner = cur >= 0 && cur != kDone;
+            const bool leaf = cur < 0;
+            const R limit = ct * R(1.0001);
+            // per-lane work: one child box (inner) or one triangle (leaf)
+            R key = m_huge<R>();
+            bool flag = false;
+            int code = 0, rank = 0, ref = 0, slot = 0;
+            R tu = R(0), tv = R(0);
+            if (inner) {
+                const V4<R> a = ldg4(&P.wide[(cur * kWide + sub) * 2]), b = ldg4(&P.wide[(cur * kWide + sub) * 2 + 1]);
+                code = child_code(a.w);
+                R tn;
+                flag = keep_box(o, k, a.x, b.x, a.y, b.y, a.z, b.z, limit, tn) && code != kEmptyChild;
+                if (flag) key = tn;
+            } else if (leaf) {
+                const int lc = ~cur, count = lc & 15;
+                slot = (lc >> 4) + sub;
+                if (sub < count) {                                    // Moeller-Trumbore, tracer.cl:640-675
+                    const V4<R> q0 = ldg4(&P.tri_test[3 * slot]), q1 = ldg4(&P.tri_test[3 * slot + 1]);
+                    const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * slot + 2].x)};
+                    const V3<R> e1 = {q0.w, q1.x, q1.y};
+                    const V3<R> dxe2 = cross(d, e2);
+                    const R det = dot(e1, dxe2);
+                    const R f = m_rcp(det);
+                    const V3<R> sv = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
+                    const R u = f * dot(sv, dxe2);
+                    const V3<R> sxe1 = cross(sv, e1);
+                    const R v = f * dot(d, sxe1);
+                    const R t = f * dot(e2, sxe1);
+                    const bool ok = !(m_abs(det) < eps) && !(u < R(0) || u > R(1)) && !(v < R(0) || (u + v) > R(1));
+                    if (ok && t > eps && t <= ct) {
+                        const int2 info = __ldg(&P.tri_info[slot]);
+                        rank = info.x; ref = info.y;
+                        flag = t < ct || rank < crank;
+                        if (flag) { key = t; tu = u; tv = v; }
+                    }
+                }
+            }
+            // nearest hit child / closest candidate of each group
+            R kmin = group_min(key);
+            unsigned sel_bits = (__ballot_sync(kFullMask, flag && key == kmin) >> gbase) & 0xffu;
+            const unsigned hit_bits = (__ballot_sync(kFullMask, flag) >> gbase) & 0xffu;
+            int sel = sel_bits ? __ffs(sel_bits) - 1 : 0;
+            const int next_code = __shfl_sync(kFullMask, code, gbase + sel);
+            int next = kDone;                                          // kDone here = "pop"
+            if (inner && hit_bits) {
+                next = next_code;
+                const unsigned others = hit_bits & ~(1u << sel);
+                if (flag && sub != sel) stk[sp + __popc(others & ((1u << sub) - 1u))] = make_int2(code, stack_key(key));
+                sp += __popc(others);
+            }
+            __syncwarp();                                              // stack writes visible to the group before any later pop
+            // leaves with candidates: verify the closest against the reference's node chain; on a rejection try the next one
+            bool pending = leaf && hit_bits != 0u;
+            while (__any_sync(kFullMask, pending)) {
+                if (__any_sync(kFullMask, pending && (sel_bits & (sel_bits - 1u)) != 0u)) {     // equal t inside a leaf: lower rank first
+                    const int rmin = group_min((flag && key == kmin) ? rank : 0x7fffffff);
+                    sel_bits = (__ballot_sync(kFullMask, flag && key == kmin && rank == rmin) >> gbase) & 0xffu;
+                    sel = sel_bits ? __ffs(sel_bits) - 1 : 0;
+                }
+                bool accepted = false;
+                if (pending && sub == sel) {
+                    accepted = reference_tests_node(P, o, d, s, ref, whole_chain);
+                    flag = false; key = m_huge<R>();                   // consumed either way
+                }
+                const unsigned acc_bits = (__ballot_sync(kFullMask, accepted) >> gbase) & 0xffu;
+                const R wt = kmin;                                   // (uniform in the group)
+                const R wu = __shfl_sync(kFullMask, tu, gbase + sel), wv = __shfl_sync(kFullMask, tv, gbase + sel);
+                const int wrank = __shfl_sync(kFullMask, rank, gbase + sel), wslot = __shfl_sync(kFullMask, slot, gbase + sel);
+                if (pending && acc_bits) { ct = wt; crank = wrank; cslot = wslot; cu = wu; cv = wv; pending = false; }
+                // rejected: the remaining candidates of this leaf
+                kmin = group_min(key);
+                sel_bits = (__ballot_sync(kFullMask, flag && key == kmin) >> gbase) & 0xffu;
+                sel = sel_bits ? __ffs(sel_bits) - 1 : 0;
+                if (sel_bits == 0u) pending = false;
+            }
+            if (cur != kDone && next == kDone) {                      // pop; children beyond the current best are dropped
+                const R lim2 = ct * R(1.0001);
+                while (sp > 0) {
+                    --sp;
+                    const int2 e = stk[sp];
+                    if (!(R(__int_as_float(e.y)) > lim2)) { next = e.x; break; }
+                }
+            }
+            cur = next;
+        }
+        // hand the results back: owner number q of this round reads group q's registers
+        const bool is_owner = ((round_bits >> lane) & 1u) != 0u;
+        const int from = is_owner ? __popc(round_bits & ((1u << lane) - 1u)) * 8 : lane;
+        const R rt = __shfl_sync(kFullMask, ct, from), ru = __shfl_sync(kFullMask, cu, from), rv = __shfl_sync(kFullMask, cv, from);
+        const int rslot = __shfl_sync(kFullMask, cslot, from);
+        if (is_owner && rslot >= 0) { h.t = rt; h.obj = j; h.tri = rslot; h.u = ru; h.v = rv; }
+    }
+}
+
+// All mesh objects of the scene (tracer.cl:598-720), after the analytic objects.  Called by all 32 lanes.
+template <typename R>
+__device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h, int2* __restrict__ stk) {
     for (int r = 0; r < P.n_runs; ++r) {
         if (P.runs[r].type != 4) continue;
         for (int j = P.runs[r].begin; j < P.runs[r].end; ++j) {
@@ -430,80 +580,12 @@ __device__ __forceinline__ bool mesh_wanted(const Params<R>& P, V3<R> ro, V3<R> 
             const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
             const Slab<R> s = make_slab(d, P.eps);
             R t0, t1, tn;
-            const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);      // NaN / inf rays hit nothing upstream
-            if (finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1) &&
-                keep_box(o, inv_dir(d), m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], best_t * R(1.0001), tn))
-                want = true;
-        }
-    }
-    return want;
-}
-
-// All mesh objects against one ray, per lane.  In: the closest analytic hit (ct, cobj).  Out: updated
-// (ct, cobj) and, when a triangle won, its slot and barycentrics.  `stk` is this thread's column of the
-// shared-memory stack (stride = block size).
-template <typename R>
-__device__ __forceinline__ void mesh_walk(const Params<R>& P, V3<R> ro, V3<R> rd, R& ct, int& cobj, int& cslot, R& cu, R& cv,
-                                          int* __restrict__ stk, int stride) {
-    const R eps = P.eps;
-    for (int r = 0; r < P.n_runs; ++r) {
-        if (P.runs[r].type != 4) continue;
-        for (int j = P.runs[r].begin; j < P.runs[r].end; ++j) {
-            const DObjHot<R>& ob = P.hot[j];
-            const DMesh<R>& m = P.mesh[j];
-            if (m.bvh_root < 0) continue;
-            const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            const Slab<R> s = make_slab(d, eps);
-            const IDir<R> k = inv_dir(d);
-            R t0, t1, tn0, tn1;
+            // object AABB under the reference rule (tracer.cl:609) AND the padded extent of the triangles within reach
+            // of the closest hit so far; NaN / inf rays hit nothing upstream
             const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);
-            if (!(finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1))) continue;   // tracer.cl:609
-            if (!keep_box(o, k, m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], ct * R(1.0001), tn0)) continue;
-            // equal t: an earlier object keeps the hit (first recorded wins), a later one loses it to this mesh
-            int crank = cobj > j ? 0x7fffffff : -1;
-            const bool whole_chain = !(m.flags & 1) || !(s.dx && s.dy && s.dz);
-            int node = m.bvh_root, sp = 0;
-            while (true) {
-                if (node >= 0) {
-                    const V4<R> na = ldg4(&P.bvh_a[node]), nb = ldg4(&P.bvh_b[node]), nc = ldg4(&P.bvh_c[node]);
-                    const int2 ch = __ldg(&P.bvh_child[node]);
-                    const R limit = ct * R(1.0001);
-                    const bool h0 = keep_box(o, k, na.x, na.y, na.z, na.w, nb.x, nb.y, limit, tn0);
-                    const bool h1 = keep_box(o, k, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, limit, tn1);
-                    if (h0 && h1) {
-                        const bool swap = tn1 < tn0;                  // nearer child first
-                        stk[sp * stride] = swap ? ch.x : ch.y; ++sp;
-                        node = swap ? ch.y : ch.x;
-                        continue;
-                    }
-                    if (h0 || h1) { node = h0 ? ch.x : ch.y; continue; }
-                } else {
-                    const int code = ~node, first = code >> 3, count = code & 7;
-                    for (int q = 0; q < count; ++q) {                   // Moeller-Trumbore, tracer.cl:640-675
-                        const int n = first + q;
-                        const V4<R> q0 = ldg4(&P.tri_test[3 * n]), q1 = ldg4(&P.tri_test[3 * n + 1]);
-                        const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * n + 2].x)};
-                        const V3<R> e1 = {q0.w, q1.x, q1.y};
-                        const V3<R> dxe2 = cross(d, e2);
-                        const R det = dot(e1, dxe2);
-                        const R f = m_rcp(det);
-                        const V3<R> sv = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
-                        const R u = f * dot(sv, dxe2);
-                        const V3<R> sxe1 = cross(sv, e1);
-                        const R v = f * dot(d, sxe1);
-                        const R t = f * dot(e2, sxe1);
-                        const bool ok = !(m_abs(det) < eps) && !(u < R(0) || u > R(1)) && !(v < R(0) || (u + v) > R(1));
-                        if (ok && t > eps && t <= ct) {
-                            const int2 info = __ldg(&P.tri_info[n]);
-                            if ((t < ct || info.x < crank) && reference_tests_node(P, o, d, s, info.y, whole_chain)) {
-                                ct = t; crank = info.x; cobj = j; cslot = n; cu = u; cv = v;
-                            }
-                        }
-                    }
-                }
-                if (sp == 0) break;
-                --sp; node = stk[sp * stride];
-            }
+            const bool want = live && finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1) &&
+                              keep_box(o, inv_dir(d), m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], h.t * R(1.0001), tn);
+            mesh_hit<R>(P, m, j, o, d, want, lane, h, stk);
         }
     }
 }
@@ -766,10 +848,14 @@ template <typename R> __device__ __forceinline__ void store_pixel(const Params<R
     }
 }
 
-// ---- kernel for scenes without meshes ------------------------------------------------------------
-template <typename R, int RNG>
+// ---- the kernel ----------------------------------------------------------------------------------
+// GROUPS = the scene contains mesh objects: only then is the cooperative BVH walk (and its shared-memory
+// stacks) compiled in.
+template <typename R, int RNG, bool GROUPS>
 __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS)) trace_kernel(const __grid_constant__ Params<R> P) {
+    __shared__ int2 mesh_stacks[GROUPS ? kBlockThreads / kWide : 1][GROUPS ? kWideStack + 1 : 1];   // one per 8-lane group
     const PixelSlot px = pixel_slot(P);
+    const int lane = threadIdx.x & 31;
     const int W = P.cam.width;
     const int slice = blockIdx.y;
     const unsigned samples = (unsigned)P.samples;
@@ -787,7 +873,8 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     s.ro = {R(0), R(0), R(0)}; s.rd = {R(0), R(0), R(0)};
     s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
     bool fresh = true;                 // need a new camera ray
-    bool live = px.has_pixel;          // false once this lane has finished all its samples
+    bool live = px.has_pixel;          // false once this lane has finished all its samples (lanes without a pixel
+                                       // stay in the loop: the mesh walk is warp-cooperative and uses all 32 lanes)
 
     // Camera rays are generated one path AHEAD and parked in registers.  Generation runs only when
     // some lane needs a ray it does not have; at that moment every lane without a parked ray makes
@@ -817,159 +904,12 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
 
         Hit<R> h;
         closest_analytic<R>(P, s.ro, s.rd, h);
+        if (GROUPS) closest_mesh<R>(P, s.ro, s.rd, live, lane, h, mesh_stacks[threadIdx.x / kWide]);
 
         bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
         if (live && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);
         if (done) {
             col_r += (double)s.accum.x; col_g += (double)s.accum.y; col_b += (double)s.accum.z;   // tracer.cl:1179
-            s.n += (unsigned)P.slices;
-            fresh = true;
-        }
-    }
-    if (px.has_pixel) store_pixel(P, px, slice, col_r, col_g, col_b);
-}
-
-// ---- kernel for scenes with meshes ---------------------------------------------------------------
-// Same segment loop, but the BVH walk is taken out of it.  Only a fraction of a warp's rays reach a mesh
-// on any given segment (ncu on the teapot scene: ~4 of 32 lanes in the walk of the previous design), so
-// walking in place leaves most lanes idle.  Instead a thread whose ray needs a mesh PARKS it in a
-// block-wide queue in shared memory and waits; the other lanes carry on with their paths.  When a
-// warp's worth of rays is queued (or nothing else can run) the block makes one BVH pass: thread k walks
-// queued ray k -- per-lane traversal of the rebuilt tree with full warps -- and writes the result to
-// the owner's slot; the owners pick their hits up and shade in the same iteration as everybody else.
-template <typename R> struct MeshShared {
-    // dynamic shared memory, T = block size:  int stack[kMeshStack][T];  R ray[7][T] (o, d, best t);
-    // int ent[2][T] (best object, owner);  R res[3][T] (t, u, v);  int resi[2][T] (object, slot);
-    // int2 tally[2][T/32];  int count
-    static __host__ __device__ size_t bytes(int T) {
-        return size_t(kMeshStack) * T * 4 + size_t(7) * T * sizeof(R) + size_t(2) * T * 4 + size_t(3) * T * sizeof(R) + size_t(2) * T * 4 +
-               size_t(2) * (T / 32) * 8 + 16;
-    }
-};
-
-#ifndef PTK_MESH_MIN_BLOCKS
-#define PTK_MESH_MIN_BLOCKS 6
-#endif
-#ifndef PTK_MESH_MIN_BLOCKS_F64
-#define PTK_MESH_MIN_BLOCKS_F64 3
-#endif
-
-template <typename R, int RNG, int T>
-__global__ void __launch_bounds__(T, ((sizeof(R) == 8 ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MESH_MIN_BLOCKS) * 128) / T)
-trace_mesh_kernel(const __grid_constant__ Params<R> P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* const q_ray = reinterpret_cast<R*>(smem_raw);                       // [7][T]
-    R* const q_res = q_ray + 7 * T;                                        // [3][T]
-    int* const q_stack = reinterpret_cast<int*>(q_res + 3 * T);            // [kMeshStack][T]
-    int* const q_ent = q_stack + kMeshStack * T;                           // [2][T]
-    int* const q_resi = q_ent + 2 * T;                                     // [2][T]
-    int2* const q_tally = reinterpret_cast<int2*>(q_resi + 2 * T);         // [2][T/32]
-    int* const q_count = reinterpret_cast<int*>(q_tally + 2 * (T / 32));
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) *q_count = 0;
-    __syncthreads();
-
-    const PixelSlot px = pixel_slot(P);
-    const int W = P.cam.width;
-    const int slice = blockIdx.y;
-    const unsigned samples = (unsigned)P.samples;
-    const double seed = px.has_pixel ? P.seeds[(size_t)px.gy * W + px.lx] : 0.0;
-    const float fgi = (float)(seed / (double)P.n_objects);     // tracer.cl:840
-    const float fgi2 = (float)(seed / (double)samples);        // tracer.cl:841
-    const R fx = R(px.lx), fy = R(px.gy);
-    const V3<R> cam_origin = {P.cam.inv[3], P.cam.inv[7], P.cam.inv[11]};
-
-    double col_r = 0.0, col_g = 0.0, col_b = 0.0;
-    Path<R> s;
-    s.n = (unsigned)(P.sample_begin + slice);
-    const unsigned n_end = (unsigned)P.sample_end;
-    s.b = 0; s.effective = 0; s.inside = false;
-    s.ro = {R(0), R(0), R(0)}; s.rd = {R(0), R(0), R(0)};
-    s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
-    bool fresh = true, live = px.has_pixel;
-    bool waiting = false;              // this thread's ray is parked in the queue
-    V3<R> nxo = cam_origin, nxd = {R(0), R(0), R(0)};
-    bool have_next = false;
-    Hit<R> h;
-    h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
-    int queued = 0;                    // rays in the queue (same value in every thread of the block)
-    int parity = 0;
-
-    while (true) {
-        if (fresh && s.n >= n_end) live = false;
-        const bool starved = fresh && live && !have_next;
-        if (__any_sync(kFullMask, starved)) {
-            const unsigned gn = fresh ? s.n : s.n + (unsigned)P.slices;
-            if (live && !have_next && gn < n_end) {
-                camera_ray<R, RNG>(P, fx, fy, fgi, fgi2, gn, cam_origin, nxo, nxd);
-                have_next = true;
-            }
-        }
-        if (fresh && live) {
-            s.ro = nxo; s.rd = nxd; have_next = false;
-            s.b = 0; s.effective = 0; s.inside = false;
-            s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
-            fresh = false;
-        }
-
-        // analytic objects for every lane that has a ray to trace; then: does a mesh have to be walked?
-        const bool run = live && !waiting;
-        Hit<R> hn;
-        closest_analytic<R>(P, s.ro, s.rd, hn);
-        if (run) h = hn;
-        const bool want = run && mesh_wanted<R>(P, s.ro, s.rd, h.t);
-        const unsigned wm = __ballot_sync(kFullMask, want);
-        if (wm) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(q_count, __popc(wm));
-            base = __shfl_sync(kFullMask, base, 0);
-            if (want) {
-                const int e = base + __popc(wm & ((1u << lane) - 1u));
-                q_ray[0 * T + e] = s.ro.x; q_ray[1 * T + e] = s.ro.y; q_ray[2 * T + e] = s.ro.z;
-                q_ray[3 * T + e] = s.rd.x; q_ray[4 * T + e] = s.rd.y; q_ray[5 * T + e] = s.rd.z;
-                q_ray[6 * T + e] = h.t;
-                q_ent[0 * T + e] = h.obj; q_ent[1 * T + e] = tid;
-                waiting = true;
-            }
-        }
-        const unsigned rm = __ballot_sync(kFullMask, live && !waiting);
-        if (lane == 0) q_tally[parity * (T / 32) + wid] = make_int2(__popc(wm), rm != 0u);
-        __syncthreads();                                             // ---- barrier A
-        bool runnable = false;
-#pragma unroll
-        for (int w = 0; w < T / 32; ++w) { const int2 v = q_tally[parity * (T / 32) + w]; queued += v.x; runnable = runnable || v.y != 0; }
-        parity ^= 1;
-        if (queued == 0 && !runnable) break;                         // every thread of the block is finished
-        bool resolved = false;
-        if (queued > 0 && (queued >= P.drain_threshold || !runnable)) {
-            if (tid == 0) *q_count = 0;                              // nobody enqueues before barrier B
-            if (tid < queued) {
-                const V3<R> wo = {q_ray[0 * T + tid], q_ray[1 * T + tid], q_ray[2 * T + tid]};
-                const V3<R> wd = {q_ray[3 * T + tid], q_ray[4 * T + tid], q_ray[5 * T + tid]};
-                R ct = q_ray[6 * T + tid], cu = R(0), cv = R(0);
-                int cobj = q_ent[0 * T + tid], cslot = -1;
-                const int owner = q_ent[1 * T + tid];
-                mesh_walk<R>(P, wo, wd, ct, cobj, cslot, cu, cv, q_stack + tid, T);
-                q_res[0 * T + owner] = ct; q_res[1 * T + owner] = cu; q_res[2 * T + owner] = cv;
-                q_resi[0 * T + owner] = cobj; q_resi[1 * T + owner] = cslot;
-            }
-            __syncthreads();                                         // ---- barrier B
-            queued = 0;
-            if (waiting) {
-                if (q_resi[1 * T + tid] >= 0) {
-                    h.t = q_res[0 * T + tid]; h.u = q_res[1 * T + tid]; h.v = q_res[2 * T + tid];
-                    h.obj = q_resi[0 * T + tid]; h.tri = q_resi[1 * T + tid];
-                }
-                waiting = false; resolved = true;
-            }
-        }
-
-        const bool ready = live && !waiting && (run || resolved);
-        bool done = ready;                       // a miss ends the path
-        if (ready && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);
-        if (done) {
-            col_r += (double)s.accum.x; col_g += (double)s.accum.y; col_b += (double)s.accum.z;
             s.n += (unsigned)P.slices;
             fresh = true;
         }

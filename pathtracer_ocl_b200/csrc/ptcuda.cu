@@ -64,8 +64,7 @@ template <typename R> struct HostScene {
     std::vector<R> lens;       // sunflower lens points, 2 per sample (empty without depth of field)
     std::vector<ptk::V4<R>> node_lo, node_hi;     // reference BVH boxes in the reference's visiting order
     std::vector<int> node_parent;
-    std::vector<ptk::V4<R>> bvh_a, bvh_b, bvh_c;  // rebuilt BVH: child boxes per node
-    std::vector<int2> bvh_child;
+    std::vector<ptk::V4<R>> wide;                 // rebuilt BVH: 8 children x (lo.xyz + child code, hi.xyz) per node
     std::vector<ptk::V4<R>> tri_test, tri_shade;  // 3 records per slot, slots in leaf order
     std::vector<int2> tri_info;                   // slot -> (rank in the reference's recording order, reference node)
     ptk::DCam<R> cam;
@@ -105,10 +104,13 @@ void collect_reference_nodes(const ptw_group* groups, int n_groups, int n_tris, 
 }
 
 // ---- rebuilt BVH ---------------------------------------------------------------------------------
-// Binary BVH over the triangles of one group object: binned surface-area heuristic, leaves of <= 4
-// triangles, built in double.  It is an INDEX only -- which triangles may be hit is still decided by the
-// reference's own arithmetic on the device -- so the one requirement is that a node's stored box
-// contains its triangles with room for the rounding of the device's slab test: boxes are padded.
+// 8-wide BVH over the triangles of one group object, for the warp-cooperative walk of trace.cuh (8 lanes
+// per ray: one child box or one leaf triangle per lane).  Built as a binary tree by the binned surface-
+// area heuristic in double (leaves of <= 8 triangles), then collapsed: a wide node adopts grandchildren,
+// largest box first, until it has 8 children.  It is an INDEX only -- which triangles may be hit is
+// still decided by the reference's own arithmetic on the device -- so the one requirement is that a
+// stored child box contains the triangles below it with room for the rounding of the device's slab
+// test: boxes are padded.
 struct Box3 {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     void add(const double* p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
@@ -121,6 +123,7 @@ struct Box3 {
     }
 };
 struct BuildPrim { Box3 box; double c[3]; RefTri ref; };
+struct BinNode { Box3 box; int left = -1, right = -1, begin = 0, end = 0; };   // left < 0: leaf over prims[begin, end)
 
 template <typename R> void padded(const Box3& b, R* lo, R* hi) {
     for (int a = 0; a < 3; ++a) {
@@ -130,39 +133,26 @@ template <typename R> void padded(const Box3& b, R* lo, R* hi) {
         if (double(hi[a]) < b.hi[a] + 0.5 * pad) hi[a] = std::nextafter(hi[a], R(1e30));
     }
 }
+inline float code_as(float, int code) { float f; std::memcpy(&f, &code, 4); return f; }   // bit pattern, never used in arithmetic
+inline double code_as(double, int code) { return double(code); }                          // exact
 
 template <typename R> struct BvhBuilder {
     const ptw_triangle* tris;
     HostScene<R>& out;
     std::vector<BuildPrim>& prims;
-    int max_depth = 0;
-    static constexpr int kBins = 32, kMaxLeaf = 4, kSahDepth = 20;
+    std::vector<BinNode> bin;
+    int wide_depth = 0, stack_need = 0;
+    static constexpr int kBins = 32, kSahDepth = 24;
 
-    int make_leaf(int begin, int end) {
-        const int first = int(out.tri_info.size());
-        for (int i = begin; i < end; ++i) {
-            const RefTri& r = prims[size_t(i)].ref;
-            const ptw_triangle& t = tris[r.src];
-            out.tri_test.push_back({R(t.p1[0]), R(t.p1[1]), R(t.p1[2]), R(t.e1[0])});
-            out.tri_test.push_back({R(t.e1[1]), R(t.e1[2]), R(t.e2[0]), R(t.e2[1])});
-            out.tri_test.push_back({R(t.e2[2]), R(0), R(0), R(0)});
-            out.tri_shade.push_back({R(t.n1[0]), R(t.n1[1]), R(t.n1[2]), R(t.color[0])});
-            out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
-            out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
-            out.tri_info.push_back(make_int2(r.rank, r.ref_node));
-        }
-        if (first >= (1 << 27)) fail("too many triangles");
-        return ~((first << 3) | (end - begin));
-    }
-
-    // Builds the subtree over prims[begin, end); returns its child code (node index, or ~leaf code) and box.
-    int build(int begin, int end, int depth, Box3& box) {
-        max_depth = std::max(max_depth, depth);
-        box = Box3();
-        Box3 cb;
+    // binary SAH tree over prims[begin, end); returns the node's index in `bin`
+    int build(int begin, int end, int depth) {
+        const int me = int(bin.size());
+        bin.emplace_back();
+        Box3 box, cb;
         for (int i = begin; i < end; ++i) { box.merge(prims[size_t(i)].box); cb.add(prims[size_t(i)].c); }
+        bin[size_t(me)].box = box; bin[size_t(me)].begin = begin; bin[size_t(me)].end = end;
         const int count = end - begin;
-        if (count <= 1) return make_leaf(begin, end);
+        if (count <= ptk::kLeafTris) return me;
         int mid = -1;
         const double ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
         if (depth < kSahDepth && (ext[0] > 0 || ext[1] > 0 || ext[2] > 0)) {
@@ -183,25 +173,21 @@ template <typename R> struct BvhBuilder {
                 for (int k = 0; k < kBins - 1; ++k) {
                     acc.merge(bb[k]); n += bn[k];
                     if (n == 0 || right_n[k + 1] == 0) continue;
-                    const double cost = acc.half_area() * n + right_area[k + 1] * right_n[k + 1];
+                    // a leaf costs one cooperative step per started group of kLeafTris triangles
+                    const double cost = acc.half_area() * std::ceil(n / double(ptk::kLeafTris)) + right_area[k + 1] * std::ceil(right_n[k + 1] / double(ptk::kLeafTris));
                     if (cost < best) { best = cost; best_axis = a; best_bin = k; }
                 }
             }
-            // leaf cost `count` vs one more node visit (1.2 triangle tests) plus the children's expected tests
-            const double parent_area = box.half_area();
-            const bool split_pays = best_axis >= 0 && (parent_area <= 0 || 1.2 + best / parent_area < double(count));
-            if (count <= kMaxLeaf && !split_pays) return make_leaf(begin, end);
             if (best_axis >= 0) {
                 const double scale = double(kBins) / ext[best_axis];
+                const double lo = cb.lo[best_axis];
                 auto it = std::partition(prims.begin() + begin, prims.begin() + end, [&](const BuildPrim& p) {
-                    int k = int((p.c[best_axis] - cb.lo[best_axis]) * scale);
+                    int k = int((p.c[best_axis] - lo) * scale);
                     k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
                     return k <= best_bin;
                 });
                 mid = int(it - prims.begin());
             }
-        } else if (count <= kMaxLeaf) {
-            return make_leaf(begin, end);
         }
         if (mid <= begin || mid >= end) {                 // no usable SAH split: object median along the widest axis
             int axis = 0;
@@ -211,17 +197,61 @@ template <typename R> struct BvhBuilder {
             std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
                              [axis](const BuildPrim& x, const BuildPrim& y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.ref.rank < y.ref.rank); });
         }
-        const int me = int(out.bvh_child.size());
-        out.bvh_a.push_back({}); out.bvh_b.push_back({}); out.bvh_c.push_back({}); out.bvh_child.push_back(make_int2(0, 0));
-        Box3 b0, b1;
-        const int c0 = build(begin, mid, depth + 1, b0);
-        const int c1 = build(mid, end, depth + 1, b1);
-        R l0[3], h0[3], l1[3], h1[3];
-        padded<R>(b0, l0, h0); padded<R>(b1, l1, h1);
-        out.bvh_a[size_t(me)] = {l0[0], h0[0], l0[1], h0[1]};
-        out.bvh_b[size_t(me)] = {l0[2], h0[2], l1[0], h1[0]};
-        out.bvh_c[size_t(me)] = {l1[1], h1[1], l1[2], h1[2]};
-        out.bvh_child[size_t(me)] = make_int2(c0, c1);
+        const int l = build(begin, mid, depth + 1);
+        const int r = build(mid, end, depth + 1);
+        bin[size_t(me)].left = l; bin[size_t(me)].right = r;
+        return me;
+    }
+
+    int make_leaf(const BinNode& n) {
+        const int first = int(out.tri_info.size());
+        for (int i = n.begin; i < n.end; ++i) {
+            const RefTri& r = prims[size_t(i)].ref;
+            const ptw_triangle& t = tris[r.src];
+            out.tri_test.push_back({R(t.p1[0]), R(t.p1[1]), R(t.p1[2]), R(t.e1[0])});
+            out.tri_test.push_back({R(t.e1[1]), R(t.e1[2]), R(t.e2[0]), R(t.e2[1])});
+            out.tri_test.push_back({R(t.e2[2]), R(0), R(0), R(0)});
+            out.tri_shade.push_back({R(t.n1[0]), R(t.n1[1]), R(t.n1[2]), R(t.color[0])});
+            out.tri_shade.push_back({R(t.n2[0]), R(t.n2[1]), R(t.n2[2]), R(t.color[1])});
+            out.tri_shade.push_back({R(t.n3[0]), R(t.n3[1]), R(t.n3[2]), R(t.color[2])});
+            out.tri_info.push_back(make_int2(r.rank, r.ref_node));
+        }
+        if (first >= (1 << 26)) fail("too many triangles");
+        return ~((first << 4) | (n.end - n.begin));
+    }
+
+    // Emits the wide node for binary node `b` (an inner node); returns its index.  `pending` = stack entries
+    // the device walk may hold when it enters this node (worst case: every sibling on the way was pushed).
+    int emit_wide(int b, int depth, int pending) {
+        wide_depth = std::max(wide_depth, depth);
+        std::vector<int> kids = {bin[size_t(b)].left, bin[size_t(b)].right};
+        while (int(kids.size()) < ptk::kWide) {
+            int pick = -1; double area = -1.0;
+            for (size_t i = 0; i < kids.size(); ++i) {
+                const BinNode& k = bin[size_t(kids[i])];
+                if (k.left >= 0 && k.box.half_area() > area) { area = k.box.half_area(); pick = int(i); }
+            }
+            if (pick < 0) break;
+            const int k = kids[size_t(pick)];
+            kids[size_t(pick)] = bin[size_t(k)].left;
+            kids.push_back(bin[size_t(k)].right);
+        }
+        const int me = int(out.wide.size()) / (2 * ptk::kWide);
+        out.wide.resize(out.wide.size() + 2 * ptk::kWide, ptk::V4<R>{R(0), R(0), R(0), R(0)});
+        const int need = pending + int(kids.size()) - 1;
+        stack_need = std::max(stack_need, need);
+        for (int c = 0; c < ptk::kWide; ++c) {
+            int code = ptk::kEmptyChild;
+            R lo[3] = {R(0), R(0), R(0)}, hi[3] = {R(0), R(0), R(0)};
+            if (c < int(kids.size())) {
+                const BinNode& k = bin[size_t(kids[size_t(c)])];
+                padded<R>(k.box, lo, hi);
+                code = k.left >= 0 ? emit_wide(kids[size_t(c)], depth + 1, need) : make_leaf(k);
+            }
+            const size_t at = (size_t(me) * ptk::kWide + size_t(c)) * 2;
+            out.wide[at] = {lo[0], lo[1], lo[2], code_as(R(0), code)};
+            out.wide[at + 1] = {hi[0], hi[1], hi[2], R(0)};
+        }
         return me;
     }
 };
@@ -256,21 +286,22 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
     }
     if (prims.empty()) { m.bvh_root = -1; return; }
     BvhBuilder<R> builder{tris, out, prims};
-    Box3 root_box;
-    int root = builder.build(0, int(prims.size()), 0, root_box);
-    if (root < 0) {                                       // a single leaf: give it a node to hang from
-        const int me = int(out.bvh_child.size());
+    const int root = builder.build(0, int(prims.size()), 0);
+    const Box3 root_box = builder.bin[size_t(root)].box;
+    if (builder.bin[size_t(root)].left < 0) {             // a single leaf: give it a node to hang from
+        const int me = int(out.wide.size()) / (2 * ptk::kWide);
+        out.wide.resize(out.wide.size() + 2 * ptk::kWide, ptk::V4<R>{R(0), R(0), R(0), code_as(R(0), ptk::kEmptyChild)});
         R lo[3], hi[3];
         padded<R>(root_box, lo, hi);
-        out.bvh_a.push_back({lo[0], hi[0], lo[1], hi[1]});
-        out.bvh_b.push_back({lo[2], hi[2], lo[0], hi[0]});
-        out.bvh_c.push_back({lo[1], hi[1], lo[2], hi[2]});
-        out.bvh_child.push_back(make_int2(root, ~0));     // second child: a leaf of zero triangles
-        root = me;
+        out.wide[size_t(me) * ptk::kWide * 2] = {lo[0], lo[1], lo[2], code_as(R(0), builder.make_leaf(builder.bin[size_t(root)]))};
+        out.wide[size_t(me) * ptk::kWide * 2 + 1] = {hi[0], hi[1], hi[2], R(0)};
+        for (int c = 1; c < ptk::kWide; ++c) out.wide[(size_t(me) * ptk::kWide + size_t(c)) * 2 + 1] = {R(0), R(0), R(0), R(0)};
+        m.bvh_root = me;
+    } else {
+        m.bvh_root = builder.emit_wide(root, 0, 0);
     }
-    if (builder.max_depth + 2 > ptk::kMeshStack) fail("object %d: rebuilt BVH is %d levels deep (limit %d)", obj_index, builder.max_depth, ptk::kMeshStack - 2);
-    out.mesh_depth = std::max(out.mesh_depth, builder.max_depth);
-    m.bvh_root = root;
+    if (builder.stack_need > ptk::kWideStack) fail("object %d: rebuilt BVH needs %d traversal stack entries (limit %d)", obj_index, builder.stack_need, ptk::kWideStack);
+    out.mesh_depth = std::max(out.mesh_depth, builder.wide_depth);
     R lo[3], hi[3];
     padded<R>(root_box, lo, hi);
     for (int a = 0; a < 3; ++a) { m.root_lo[a] = lo[a]; m.root_hi[a] = hi[a]; }
@@ -363,7 +394,7 @@ struct DeviceState {
     cudaMemPool_t pool = nullptr;   // stream-ordered pool (single-GPU contexts), else plain cudaMalloc
     void* shade = nullptr; void* lens = nullptr; void* mesh = nullptr;
     void* node_lo = nullptr; void* node_hi = nullptr; void* node_parent = nullptr;
-    void* bvh_a = nullptr; void* bvh_b = nullptr; void* bvh_c = nullptr; void* bvh_child = nullptr;
+    void* wide = nullptr;
     void* tri_test = nullptr; void* tri_shade = nullptr; void* tri_info = nullptr;
     void* tex[3] = {nullptr, nullptr, nullptr};
     double* seeds = nullptr;
@@ -373,8 +404,6 @@ struct DeviceState {
     double* acc = nullptr;          // rows*W*4 running sums of a progressive render
     uchar4* rgba8 = nullptr;        // rows*W tone-mapped bytes (ptc_read_rgba8)
     int slices = 1;
-    int mesh_block = 256;           // threads per block of the mesh kernel (128 or 256)
-    int drain_threshold = 64;       // queued rays that trigger a BVH pass
     int sm_count = 0;
     float last_ms = 0.f;
 };
@@ -448,10 +477,7 @@ template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const Ho
     d.node_hi = upload(d, s.node_hi, h2d);
     d.node_parent = upload(d, s.node_parent, h2d);
     d.mesh = upload(d, s.mesh, h2d);
-    d.bvh_a = upload(d, s.bvh_a, h2d);
-    d.bvh_b = upload(d, s.bvh_b, h2d);
-    d.bvh_c = upload(d, s.bvh_c, h2d);
-    d.bvh_child = upload(d, s.bvh_child, h2d);
+    d.wide = upload(d, s.wide, h2d);
     d.tri_test = upload(d, s.tri_test, h2d);
     d.tri_shade = upload(d, s.tri_shade, h2d);
     d.tri_info = upload(d, s.tri_info, h2d);
@@ -471,10 +497,7 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     P.node_hi = static_cast<const ptk::V4<R>*>(d.node_hi);
     P.node_parent = static_cast<const int*>(d.node_parent);
     P.mesh = static_cast<const ptk::DMesh<R>*>(d.mesh);
-    P.bvh_a = static_cast<const ptk::V4<R>*>(d.bvh_a);
-    P.bvh_b = static_cast<const ptk::V4<R>*>(d.bvh_b);
-    P.bvh_c = static_cast<const ptk::V4<R>*>(d.bvh_c);
-    P.bvh_child = static_cast<const int2*>(d.bvh_child);
+    P.wide = static_cast<const ptk::V4<R>*>(d.wide);
     P.tri_test = static_cast<const ptk::V4<R>*>(d.tri_test);
     P.tri_shade = static_cast<const ptk::V4<R>*>(d.tri_shade);
     P.tri_info = static_cast<const int2*>(d.tri_info);
@@ -515,28 +538,15 @@ template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScen
     bool meshes = false;
     for (int i = 0; i < c.n_objects; ++i) meshes = meshes || s.mesh[size_t(i)].bvh_root >= 0;
     const bool fast = c.rng_mode == PTC_RNG_FAST;
+    const int warps_per_block = ptk::kBlockThreads / 32;
+    dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
+    dim3 block(ptk::kBlockThreads, 1, 1);
     if (meshes) {
-        // scenes with meshes: block-wide ray queue, see trace_mesh_kernel
-        int threads = d.mesh_block;
-        P.drain_threshold = d.drain_threshold;
-        const int warps_per_block = threads / 32;
-        dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
-        const size_t smem = ptk::MeshShared<R>::bytes(threads);
-        auto go = [&](auto kernel) {
-            CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            kernel<<<grid, dim3((unsigned)threads, 1, 1), smem, d.stream>>>(P);
-        };
-        if (threads == 256) {
-            if (fast) go(ptk::trace_mesh_kernel<R, ptk::RNG_FAST, 256>); else go(ptk::trace_mesh_kernel<R, ptk::RNG_PARITY, 256>);
-        } else {
-            if (fast) go(ptk::trace_mesh_kernel<R, ptk::RNG_FAST, 128>); else go(ptk::trace_mesh_kernel<R, ptk::RNG_PARITY, 128>);
-        }
+        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, true><<<grid, block, 0, d.stream>>>(P);
+        else ptk::trace_kernel<R, ptk::RNG_PARITY, true><<<grid, block, 0, d.stream>>>(P);
     } else {
-        const int warps_per_block = ptk::kBlockThreads / 32;
-        dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
-        dim3 block(ptk::kBlockThreads, 1, 1);
-        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST><<<grid, block, 0, d.stream>>>(P);
-        else ptk::trace_kernel<R, ptk::RNG_PARITY><<<grid, block, 0, d.stream>>>(P);
+        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, false><<<grid, block, 0, d.stream>>>(P);
+        else ptk::trace_kernel<R, ptk::RNG_PARITY, false><<<grid, block, 0, d.stream>>>(P);
     }
     CUDA_OK(cudaGetLastError());
     c.stats.kernel_launches++;
@@ -675,8 +685,6 @@ ptc_context* open_impl(const ptc_job& job) {
         if (sl > 32) sl = 32;
         if (sl < 1) sl = 1;
         d.slices = int(sl);
-        if (const char* ov = std::getenv("PTC_MESH_BLOCK")) d.mesh_block = std::atoi(ov) == 128 ? 128 : 256;   // tuning overrides
-        if (const char* ov = std::getenv("PTC_MESH_DRAIN")) d.drain_threshold = std::max(1, std::atoi(ov));
     }
     if (nd > 1) {
         DeviceState& d0 = c.dev[0];
@@ -996,7 +1004,7 @@ int ptc_debug_noise3d(const float* xyz, int n, int rng_mode, float* out, char* e
 // Test hook (not part of the drop-in surface; host only, no device needed): flattens the job's scene in
 // double and copies one array of the rebuilt mesh index out, so tests can check the builder's invariants
 // (every triangle in exactly one leaf, child boxes containing their triangles, depth) and replay the walk.
-// what: 0 bvh_a, 1 bvh_b, 2 bvh_c, 3 bvh_child, 4 tri_info, 5 tri_test, 6 node_lo, 7 node_hi, 8 node_parent,
+// what: 0 wide nodes (8 children x 2 records of 4 doubles: lo.xyz + child code, hi.xyz + 0), 4 tri_info, 5 tri_test, 6 node_lo, 7 node_hi, 8 node_parent,
 // 9 mesh records (8 doubles per object: root_lo, root_hi, bvh_root, flags), 10 object node ranges (2 ints per object).
 // Returns the array's size in bytes (copying at most cap_bytes), or -1 with a message.
 int64_t ptc_debug_mesh_index(const ptc_job* job, int what, void* out, int64_t cap_bytes, char* err, int errlen) {
@@ -1017,10 +1025,7 @@ int64_t ptc_debug_mesh_index(const ptc_job* job, int what, void* out, int64_t ca
         }
         const void* src = nullptr;
         switch (what) {
-            case 0: src = hs.bvh_a.data(); bytes = int64_t(hs.bvh_a.size() * sizeof(hs.bvh_a[0])); break;
-            case 1: src = hs.bvh_b.data(); bytes = int64_t(hs.bvh_b.size() * sizeof(hs.bvh_b[0])); break;
-            case 2: src = hs.bvh_c.data(); bytes = int64_t(hs.bvh_c.size() * sizeof(hs.bvh_c[0])); break;
-            case 3: src = hs.bvh_child.data(); bytes = int64_t(hs.bvh_child.size() * sizeof(int2)); break;
+            case 0: src = hs.wide.data(); bytes = int64_t(hs.wide.size() * sizeof(hs.wide[0])); break;
             case 4: src = hs.tri_info.data(); bytes = int64_t(hs.tri_info.size() * sizeof(int2)); break;
             case 5: src = hs.tri_test.data(); bytes = int64_t(hs.tri_test.size() * sizeof(hs.tri_test[0])); break;
             case 6: src = hs.node_lo.data(); bytes = int64_t(hs.node_lo.size() * sizeof(hs.node_lo[0])); break;

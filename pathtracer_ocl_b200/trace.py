@@ -320,8 +320,7 @@ def debug_noise3d(xyz: np.ndarray, rng_mode: int = RNG_PARITY) -> np.ndarray:
 
 
 _MESH_INDEX_ARRAYS = {  # name -> (selector, dtype, trailing shape)
-    "bvh_a": (0, np.float64, (4,)), "bvh_b": (1, np.float64, (4,)), "bvh_c": (2, np.float64, (4,)),
-    "bvh_child": (3, np.int32, (2,)), "tri_info": (4, np.int32, (2,)), "tri_test": (5, np.float64, (3, 4)),
+    "wide": (0, np.float64, (4,)), "tri_info": (4, np.int32, (2,)), "tri_test": (5, np.float64, (3, 4)),
     "node_lo": (6, np.float64, (4,)), "node_hi": (7, np.float64, (4,)), "node_parent": (8, np.int32, ()),
     "mesh": (9, np.float64, (8,)), "node_range": (10, np.int32, (2,)),
 }

@@ -14,7 +14,8 @@ import pytest
 from pathtracer_ocl_b200 import scene as S, trace as T
 
 EPS = 1e-4
-MESH_STACK = 40            # trace.cuh: kMeshStack
+WIDE, LEAF_TRIS, WIDE_STACK = 8, 8, 64   # trace.cuh: kWide, kLeafTris, kWideStack
+EMPTY = -(1 << 31)                       # trace.cuh: kEmptyChild
 SLACK = 1e-13              # trace.cuh: box_slack<double>()
 
 
@@ -26,15 +27,21 @@ def index_of(scene):
 
 def leaf_slots(code):
     c = ~int(code)
-    return c >> 3, c & 7
+    return c >> 4, c & 15
 
 
-def subtree(m, child, depth, seen, depth_max):
+def children(m, node):
+    """[(code, lo, hi)] of the non-empty children of a wide node."""
+    rec = m["wide"][node * WIDE * 2:(node + 1) * WIDE * 2].reshape(WIDE, 2, 4)
+    return [(int(rec[c, 0, 3]), rec[c, 0, :3], rec[c, 1, :3]) for c in range(WIDE) if int(rec[c, 0, 3]) != EMPTY]
+
+
+def subtree(m, child, depth, pending, seen, worst):
     """Returns (lo, hi) of the triangle vertices below `child`; checks stored boxes on the way."""
-    depth_max[0] = max(depth_max[0], depth)
+    worst["depth"] = max(worst["depth"], depth)
     if child < 0:
         first, count = leaf_slots(child)
-        assert count <= 4
+        assert 1 <= count <= LEAF_TRIS
         lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
         for n in range(first, first + count):
             assert not seen[n]
@@ -46,13 +53,13 @@ def subtree(m, child, depth, seen, depth_max):
             for v in (p1, p1 + e1, p1 + e2):
                 lo, hi = np.minimum(lo, v), np.maximum(hi, v)
         return lo, hi
-    a, b, c = m["bvh_a"][child], m["bvh_b"][child], m["bvh_c"][child]
-    boxes = ((np.array([a[0], a[2], b[0]]), np.array([a[1], a[3], b[1]])), (np.array([b[2], c[0], c[2]]), np.array([b[3], c[1], c[3]])))
+    kids = children(m, child)
+    assert 1 <= len(kids) <= WIDE
+    worst["stack"] = max(worst["stack"], pending + len(kids) - 1)
     lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
-    for k in range(2):
-        clo, chi = subtree(m, int(m["bvh_child"][child, k]), depth + 1, seen, depth_max)
-        if np.isfinite(clo).all():
-            assert (boxes[k][0] < clo).all() and (boxes[k][1] > chi).all(), "stored child box must strictly contain its triangles"
+    for code, blo, bhi in kids:
+        clo, chi = subtree(m, code, depth + 1, pending + len(kids) - 1, seen, worst)
+        assert (blo < clo).all() and (bhi > chi).all(), "stored child box must strictly contain its triangles"
         lo, hi = np.minimum(lo, clo), np.maximum(hi, chi)
     return lo, hi
 
@@ -65,10 +72,12 @@ def test_builder_invariants(name):
     assert n == sc.n_triangles
     assert sorted(m["tri_info"][:, 0].tolist()) == list(range(n)), "ranks are a permutation of the recording order"
     seen = np.zeros(n, dtype=bool)
-    depth_max = [0]
-    lo, hi = subtree(m, int(m["mesh"][obj, 6]), 0, seen, depth_max)
+    worst = {"depth": 0, "stack": 0}
+    lo, hi = subtree(m, int(m["mesh"][obj, 6]), 0, 0, seen, worst)
     assert seen.all(), "every triangle sits in exactly one leaf"
-    assert depth_max[0] + 2 <= MESH_STACK
+    assert worst["stack"] <= WIDE_STACK
+    n_nodes = m["wide"].shape[0] // (2 * WIDE)
+    print(f"{name}: {n} triangles, {n_nodes} wide nodes, depth {worst['depth']}, worst-case stack {worst['stack']}")
     assert (m["mesh"][obj, 0:3] < lo).all() and (m["mesh"][obj, 3:6] > hi).all()
     # reference nodes: parents precede children (pre-order), triangles point at existing nodes
     par = m["node_parent"]
@@ -151,6 +160,9 @@ def chain_ok(m, o, d, g, whole_chain):
 
 
 def replayed_winner(m, mesh_row, obj_lo, obj_hi, o, d, best_t, stats):
+    """trace.cuh mesh_hit for one ray: at an inner node all children are tested, the nearest is entered and the other
+    hits are stacked with their entry distance; at a leaf the candidates are tried closest first (rank on ties) and
+    the first one the reference would have tested wins; stacked children beyond the best hit are dropped."""
     if not np.isfinite(o).all() or not np.isfinite(d).all():
         return -1, best_t
     if not ref_box(o, d, obj_lo[None, :], obj_hi[None, :])[0]:
@@ -163,38 +175,45 @@ def replayed_winner(m, mesh_row, obj_lo, obj_hi, o, d, best_t, stats):
     nested = int(mesh_row[7]) & 1
     whole_chain = (not nested) or not (np.abs(d) >= EPS).all()
     ct, crank, cslot = best_t, -1, -1
-    node, stack = int(mesh_row[6]), []
-    while True:
-        if node >= 0:
+    cur, stack = int(mesh_row[6]), []
+    while cur is not None:
+        nxt = None
+        if cur >= 0:
             stats["nodes"] += 1
-            a, b, c = m["bvh_a"][node], m["bvh_b"][node], m["bvh_c"][node]
-            ch = m["bvh_child"][node]
-            lim = ct * 1.0001
-            h0, tn0 = keep_box(o, k, np.array([a[0], a[2], b[0]]), np.array([a[1], a[3], b[1]]), lim)
-            h1, tn1 = keep_box(o, k, np.array([b[2], c[0], c[2]]), np.array([b[3], c[1], c[3]]), lim)
-            if h0 and h1:
-                swap = tn1 < tn0
-                stack.append(int(ch[0] if swap else ch[1]))
-                assert len(stack) <= MESH_STACK
-                node = int(ch[1] if swap else ch[0])
-                continue
-            if h0 or h1:
-                node = int(ch[0] if h0 else ch[1])
-                continue
+            hits = []
+            for lane, (code, lo, hi) in enumerate(children(m, cur)):
+                keep, tn = keep_box(o, k, lo, hi, ct * 1.0001)
+                if keep:
+                    hits.append((tn, lane, code))
+            if hits:
+                sel = min(hits)                                      # smallest tn, lowest lane on ties
+                nxt = sel[2]
+                for tn, lane, code in hits:                          # pushed in lane order
+                    if lane != sel[1]:
+                        stack.append((code, np.float32(np.nextafter(np.float32(tn), np.float32(-np.inf))) if np.float32(tn) > tn else np.float32(tn)))
+                assert len(stack) <= WIDE_STACK
         else:
-            first, count = leaf_slots(node)
-            if count:
-                stats["tris"] += count
-                ok, t, _, _ = moller_trumbore(o, d, m["tri_test"][first:first + count])
-                for q in range(count):
-                    n = first + q
-                    if ok[q] and t[q] > EPS and t[q] <= ct:
-                        rank, ref = m["tri_info"][n]
-                        if (t[q] < ct or rank < crank) and chain_ok(m, o, d, int(ref), whole_chain):
-                            ct, crank, cslot = float(t[q]), int(rank), n
-        if not stack:
-            break
-        node = stack.pop()
+            first, count = leaf_slots(cur)
+            stats["leaves"] += 1
+            ok, t, _, _ = moller_trumbore(o, d, m["tri_test"][first:first + count])
+            cands = []
+            for q in range(count):
+                n = first + q
+                if ok[q] and t[q] > EPS and t[q] <= ct:
+                    rank, ref = m["tri_info"][n]
+                    if t[q] < ct or rank < crank:
+                        cands.append((float(t[q]), int(rank), n, int(ref)))
+            for tq, rank, n, ref in sorted(cands):
+                if chain_ok(m, o, d, ref, whole_chain):
+                    ct, crank, cslot = tq, rank, n
+                    break
+        if nxt is None:
+            while stack:
+                code, tn = stack.pop()
+                if not (float(tn) > ct * 1.0001):
+                    nxt = code
+                    break
+        cur = nxt
     return cslot, ct
 
 
@@ -246,7 +265,7 @@ def test_replayed_walk_picks_the_reference_winner(name, n_rays):
     ob = sc.objects_view()[obj]
     obj_lo, obj_hi = np.array(ob["bb_min"][:3]), np.array(ob["bb_max"][:3])
     rng = np.random.default_rng(7)
-    stats = {"nodes": 0, "tris": 0}
+    stats = {"nodes": 0, "leaves": 0}
     hits = 0
     for i, (o, d) in enumerate(rays_for(m, obj_lo, obj_hi, rng, n_rays)):
         best_t = 1024.0 if i % 3 else float(rng.uniform(0.5, 30.0))      # sometimes an analytic hit limits the search
@@ -255,7 +274,7 @@ def test_replayed_walk_picks_the_reference_winner(name, n_rays):
         assert got == want, f"ray {i}: replay {got} vs reference {want} (o={o}, d={d})"
         hits += want[0] >= 0
     assert hits > n_rays // 4
-    print(f"{name}: {hits}/{n_rays} rays hit; {stats['nodes'] / n_rays:.1f} nodes and {stats['tris'] / n_rays:.1f} triangle tests per ray "
+    print(f"{name}: {hits}/{n_rays} rays hit; {stats['nodes'] / n_rays:.1f} inner and {stats['leaves'] / n_rays:.1f} leaf steps per ray "
           f"(the reference walk tests every triangle of every node it enters)")
 
 
@@ -287,7 +306,7 @@ def test_flat_reference_boxes_hide_their_triangles():
     flat = np.flatnonzero((m["node_lo"][:, :3] == m["node_hi"][:, :3]).any(axis=1))
     assert flat.size > 0, "the scene is meant to contain a flat node box"
     rng = np.random.default_rng(3)
-    stats = {"nodes": 0, "tris": 0}
+    stats = {"nodes": 0, "leaves": 0}
     seen_hidden = 0
     for i in range(300):
         o = np.array([rng.uniform(-0.9, 0.9), rng.uniform(1.5, 3.0), rng.uniform(-0.9, 0.9)])
