@@ -45,6 +45,9 @@ namespace ptk {
 #ifndef PTK_MIN_BLOCKS_F64
 #define PTK_MIN_BLOCKS_F64 3
 #endif
+#ifndef PTK_MESH_MIN_BLOCKS
+#define PTK_MESH_MIN_BLOCKS 8
+#endif
 #ifndef PTK_UNROLL_SLOTS
 // Compile-time object slots (constant-bank immediates instead of indexed constant loads) for mesh-free
 // scenes.  Measured on B200: SLOWER than the run loop (9.36 vs 10.64 Gpaths/s on the reference scene --
@@ -852,7 +855,7 @@ template <typename R> __device__ __forceinline__ void store_pixel(const Params<R
 // GROUPS = the scene contains mesh objects: only then is the cooperative BVH walk (and its shared-memory
 // stacks) compiled in.
 template <typename R, int RNG, bool GROUPS>
-__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS)) trace_kernel(const __grid_constant__ Params<R> P) {
+__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
     __shared__ int2 mesh_stacks[GROUPS ? kBlockThreads / kWide : 1][GROUPS ? kWideStack + 1 : 1];   // one per 8-lane group
     const PixelSlot px = pixel_slot(P);
     const int lane = threadIdx.x & 31;
