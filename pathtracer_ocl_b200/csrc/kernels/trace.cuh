@@ -160,7 +160,7 @@ template <typename R> struct alignas(16) DMesh {
 
 constexpr int kWide = 8;                       // children per node = lanes per ray in the cooperative walk
 constexpr int kLeafTris = 8;                   // triangles per leaf (one per lane)
-constexpr int kWideStack = 64;                 // deferred-child stack entries per ray (the host refuses trees that need more)
+constexpr int kWideStack = 96;                 // deferred-child stack entries per ray (the host refuses trees that need more)
 constexpr int kEmptyChild = (int)0x80000000;
 
 template <typename R> struct Params {

@@ -123,7 +123,7 @@ struct Box3 {
     }
 };
 struct BuildPrim { Box3 box; double c[3]; RefTri ref; };
-struct BinNode { Box3 box; int left = -1, right = -1, begin = 0, end = 0; };   // left < 0: leaf over prims[begin, end)
+struct BinNode { Box3 box; int left = -1, right = -1, begin = 0, end = 0, height = 0; };   // left < 0: leaf over prims[begin, end)
 
 template <typename R> void padded(const Box3& b, R* lo, R* hi) {
     for (int a = 0; a < 3; ++a) {
@@ -200,6 +200,7 @@ template <typename R> struct BvhBuilder {
         const int l = build(begin, mid, depth + 1);
         const int r = build(mid, end, depth + 1);
         bin[size_t(me)].left = l; bin[size_t(me)].right = r;
+        bin[size_t(me)].height = 1 + std::max(bin[size_t(l)].height, bin[size_t(r)].height);
         return me;
     }
 
@@ -225,11 +226,19 @@ template <typename R> struct BvhBuilder {
     int emit_wide(int b, int depth, int pending) {
         wide_depth = std::max(wide_depth, depth);
         std::vector<int> kids = {bin[size_t(b)].left, bin[size_t(b)].right};
+        // Every child beyond the one being walked may sit on the device's traversal stack.  Invariant: pending +
+        // height(subtree) <= kWideStack, where height is that of the BINARY subtree -- it holds at the root (the binary
+        // depth is capped) and a node only adopts grandchildren while it keeps holding for every child, so even the most
+        // lopsided tree fits the device stack: deep down the nodes simply get narrower.
         while (int(kids.size()) < ptk::kWide) {
             int pick = -1; double area = -1.0;
             for (size_t i = 0; i < kids.size(); ++i) {
                 const BinNode& k = bin[size_t(kids[i])];
-                if (k.left >= 0 && k.box.half_area() > area) { area = k.box.half_area(); pick = int(i); }
+                if (k.left < 0 || !(k.box.half_area() > area)) continue;
+                int tallest = std::max(bin[size_t(k.left)].height, bin[size_t(k.right)].height);
+                for (size_t q = 0; q < kids.size(); ++q) if (q != i) tallest = std::max(tallest, bin[size_t(kids[q])].height);
+                if (pending + int(kids.size()) + tallest > ptk::kWideStack) continue;          // (|kids| + 1 children -> |kids| pushed)
+                area = k.box.half_area(); pick = int(i);
             }
             if (pick < 0) break;
             const int k = kids[size_t(pick)];
@@ -287,6 +296,7 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
     if (prims.empty()) { m.bvh_root = -1; return; }
     BvhBuilder<R> builder{tris, out, prims};
     const int root = builder.build(0, int(prims.size()), 0);
+    if (builder.bin[size_t(root)].height > ptk::kWideStack) fail("object %d: triangle tree is %d levels deep (limit %d)", obj_index, builder.bin[size_t(root)].height, ptk::kWideStack);
     const Box3 root_box = builder.bin[size_t(root)].box;
     if (builder.bin[size_t(root)].left < 0) {             // a single leaf: give it a node to hang from
         const int me = int(out.wide.size()) / (2 * ptk::kWide);

@@ -14,7 +14,7 @@ import pytest
 from pathtracer_ocl_b200 import scene as S, trace as T
 
 EPS = 1e-4
-WIDE, LEAF_TRIS, WIDE_STACK = 8, 8, 64   # trace.cuh: kWide, kLeafTris, kWideStack
+WIDE, LEAF_TRIS, WIDE_STACK = 8, 8, 96   # trace.cuh: kWide, kLeafTris, kWideStack
 EMPTY = -(1 << 31)                       # trace.cuh: kEmptyChild
 SLACK = 1e-13              # trace.cuh: box_slack<double>()
 
@@ -321,3 +321,35 @@ def test_flat_reference_boxes_hide_their_triangles():
             seen_hidden += 1
             assert want[0] < 0 or not under_flat[want[0]]
     assert seen_hidden > 100
+
+
+def geometric_mesh(n, ratio):
+    """n small triangles whose positions and sizes shrink geometrically: SAH splits peel them off a few at a time,
+    the deepest trees a sane builder produces."""
+    lines = []
+    for k in range(n):
+        x = ratio ** k
+        s = 0.3 * x
+        lines += [f"v {x} 0 0", f"v {x + s} {s} 0", f"v {x} {s} {s}"]
+    lines.append("g spiral")
+    lines += [f"f {3 * k + 1} {3 * k + 2} {3 * k + 3}" for k in range(n)]
+    return S.scene_from_obj("\n".join(lines) + "\n", divide_threshold=50)[0]
+
+
+@pytest.mark.parametrize("n,ratio", [(600, 0.95), (3000, 0.99)])
+def test_degenerate_mesh_stays_within_the_device_stack(n, ratio):
+    sc = geometric_mesh(n, ratio)
+    m, obj = index_of(sc)
+    seen = np.zeros(m["tri_info"].shape[0], dtype=bool)
+    worst = {"depth": 0, "stack": 0}
+    subtree(m, int(m["mesh"][obj, 6]), 0, 0, seen, worst)
+    assert seen.all()
+    assert worst["stack"] <= WIDE_STACK, worst
+    print(f"geometric mesh n={n}: depth {worst['depth']}, worst-case stack {worst['stack']}")
+    # and the walk still finds the reference's winner
+    ob = sc.objects_view()[obj]
+    obj_lo, obj_hi = np.array(ob["bb_min"][:3]), np.array(ob["bb_max"][:3])
+    rng = np.random.default_rng(5)
+    stats = {"nodes": 0, "leaves": 0}
+    for i, (o, d) in enumerate(rays_for(m, obj_lo, obj_hi, rng, 120)):
+        assert replayed_winner(m, m["mesh"][obj], obj_lo, obj_hi, o, d, 1024.0, stats) == reference_winner(m, obj_lo, obj_hi, o, d, 1024.0)
