@@ -15,8 +15,9 @@ def timing(name, W, H, spp, ap=0.0, fl=0.0, prec=T.FP32, reps=3):
         st = ctx.stats()
     return st["paths"] / best / 1e3
 
-spp = int(os.environ.get("MESH_SPP", "32"))
-print(f"teapot {timing('teapot', 1280, 960, spp):8.1f}  gopher {timing('gopher', 1280, 960, spp):8.1f}  "
-      f"cubemap {timing('cubemap', 1280, 960, spp):8.1f}  reference {timing('reference', 1280, 960, 128, 0.15, 1.6):8.1f}  Mpaths/s (fp32)", flush=True)
-if os.environ.get("MESH_FP64"):
+if __name__ == "__main__":
+  spp = int(os.environ.get("MESH_SPP", "32"))
+  print(f"teapot {timing('teapot', 1280, 960, spp):8.1f}  gopher {timing('gopher', 1280, 960, spp):8.1f}  "
+        f"cubemap {timing('cubemap', 1280, 960, spp):8.1f}  reference {timing('reference', 1280, 960, 128, 0.15, 1.6):8.1f}  Mpaths/s (fp32)", flush=True)
+  if os.environ.get("MESH_FP64"):
     print(f"fp64: teapot {timing('teapot', 1280, 960, 8, prec=T.FP64):8.1f}  gopher {timing('gopher', 1280, 960, 8, prec=T.FP64):8.1f}  Mpaths/s", flush=True)
