@@ -688,11 +688,18 @@ ptc_context* open_impl(const ptc_job& job) {
         // Measured on B200 (tools/slices_time.py): blocks that live for the whole frame leave a long
         // tail (a 1/8-frame shard ran 36.3 ms with 1 slice, 29.3 ms with 32), so aim for ~16x the
         // resident thread capacity in total threads.
-        const long long want = (long long)d.sm_count * 2048 * 16;
+        // Scenes with meshes have very uneven pixels (a warp on the mesh runs several times longer than one on a
+        // wall): finer slices even the load out -- measured at 1280x960@256: teapot 2.83 Gpaths/s with 4 slices,
+        // 3.12 with 32; cubemap+gopher 4.84 -> 6.68 -- so they get 8x the thread count of analytic scenes.
+        bool meshes = false;
+        for (int k = 0; k < c.n_objects; ++k)
+            meshes = meshes || (c.precision == PTC_FP64 ? c.scene64.mesh[size_t(k)].bvh_root >= 0 : c.scene32.mesh[size_t(k)].bvh_root >= 0);
+        const long long want = (long long)d.sm_count * 2048 * (meshes ? 128 : 16);
         long long sl = px ? (want + (long long)px - 1) / (long long)px : 1;
-        if (const char* ov = std::getenv("PTC_SLICES")) sl = std::atoll(ov);    // tuning override
+        long long cap = meshes ? 64 : 32;
+        if (const char* ov = std::getenv("PTC_SLICES")) { sl = std::atoll(ov); cap = 4096; }    // tuning override
         if (sl > c.samples) sl = c.samples;
-        if (sl > 32) sl = 32;
+        if (sl > cap) sl = cap;
         if (sl < 1) sl = 1;
         d.slices = int(sl);
     }
