@@ -13,3 +13,7 @@ done
 for sc in textures envmap cubemap; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus $NG --steps 2 --warmup 3 --scene $sc --width 3840 --height 2160 --samples 4096 --aperture 0 --focal-length 0 --no-cpu-baseline 2>/dev/null | grep '^{' | tee gpurun_out/cfg5_${sc}_$NG.json | cut -c1-300
 done
+# BASELINE configs 3 and 4 (mesh scenes, full 2048 spp) on all GPUs
+for sc in teapot gopher; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus $NG --steps 3 --warmup 3 --scene $sc --aperture 0 --focal-length 0 --no-cpu-baseline 2>/dev/null | grep '^{' | tee gpurun_out/${sc}_$NG.json | cut -c1-300
+done
