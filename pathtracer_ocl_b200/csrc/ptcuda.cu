@@ -142,7 +142,12 @@ template <typename R> struct BvhBuilder {
     std::vector<BuildPrim>& prims;
     std::vector<BinNode> bin;
     int wide_depth = 0, stack_need = 0;
+    int bin_leaf = ptk::kLeafTris;      // triangles per leaf of the BINARY tree (1..kLeafTris); the optimal collapse wants a fine tree
+    bool optimal = true;                // collapse by dynamic programming (see plan()); false: greedily by area
     static constexpr int kBins = 32, kSahDepth = 24;
+    // plan(): cost[n][i] = cheapest way to present binary subtree n as at most i+1 wide-BVH roots (i = 0..6)
+    struct Plan { double cost[7]; signed char split[9]; bool leaf; };   // split[j]: roots given to the left child when n gets j (0 = "as j-1")
+    std::vector<Plan> plans;
 
     // binary SAH tree over prims[begin, end); returns the node's index in `bin`
     int build(int begin, int end, int depth) {
@@ -152,7 +157,7 @@ template <typename R> struct BvhBuilder {
         for (int i = begin; i < end; ++i) { box.merge(prims[size_t(i)].box); cb.add(prims[size_t(i)].c); }
         bin[size_t(me)].box = box; bin[size_t(me)].begin = begin; bin[size_t(me)].end = end;
         const int count = end - begin;
-        if (count <= ptk::kLeafTris) return me;
+        if (count <= bin_leaf) return me;
         int mid = -1;
         const double ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
         if (depth < kSahDepth && (ext[0] > 0 || ext[1] > 0 || ext[2] > 0)) {
@@ -173,8 +178,8 @@ template <typename R> struct BvhBuilder {
                 for (int k = 0; k < kBins - 1; ++k) {
                     acc.merge(bb[k]); n += bn[k];
                     if (n == 0 || right_n[k + 1] == 0) continue;
-                    // a leaf costs one cooperative step per started group of kLeafTris triangles
-                    const double cost = acc.half_area() * std::ceil(n / double(ptk::kLeafTris)) + right_area[k + 1] * std::ceil(right_n[k + 1] / double(ptk::kLeafTris));
+                    // a leaf costs one cooperative step per started group of bin_leaf triangles
+                    const double cost = acc.half_area() * std::ceil(n / double(bin_leaf)) + right_area[k + 1] * std::ceil(right_n[k + 1] / double(bin_leaf));
                     if (cost < best) { best = cost; best_axis = a; best_bin = k; }
                 }
             }
@@ -221,20 +226,70 @@ template <typename R> struct BvhBuilder {
         return ~((first << 4) | (n.end - n.begin));
     }
 
+    // Optimal collapse (after Ylitie, Karras, Laine 2017, "Efficient incoherent ray traversal on GPUs through compressed
+    // wide BVHs", sec. 3.1), with this walk's cost model: one cooperative step per visited wide node (kNodeCost) and per
+    // visited leaf of <= kLeafTris triangles (kLeafCost), each weighted by the surface area of its box.
+    static constexpr double kNodeCost = 1.0, kLeafCost = 1.25;
+    void plan(int n) {
+        const BinNode& b = bin[size_t(n)];
+        Plan& p = plans[size_t(n)];
+        const double area = b.box.half_area();
+        const int count = b.end - b.begin;
+        const double as_leaf = count <= ptk::kLeafTris ? area * kLeafCost : 1e300;
+        std::memset(p.split, 0, sizeof p.split);
+        if (b.left < 0) { for (double& c : p.cost) c = as_leaf; p.leaf = true; return; }
+        plan(b.left); plan(b.right);
+        const Plan &l = plans[size_t(b.left)], &r = plans[size_t(b.right)];
+        auto distribute = [&](int j, signed char& k_best) {          // best split of j roots between the two children
+            double best = 1e300;
+            for (int k = 1; k < j; ++k) {
+                const double c = l.cost[std::min(k, 7) - 1] + r.cost[std::min(j - k, 7) - 1];
+                if (c < best) { best = c; k_best = (signed char)k; }
+            }
+            return best;
+        };
+        signed char k8 = 1;
+        const double as_inner = area * kNodeCost + distribute(ptk::kWide, k8);
+        p.split[8] = k8;
+        p.leaf = as_leaf <= as_inner;
+        p.cost[0] = std::min(as_leaf, as_inner);
+        for (int i = 2; i <= 7; ++i) {
+            signed char k = 1;
+            const double d = distribute(i, k);
+            if (d < p.cost[i - 2]) { p.cost[i - 1] = d; p.split[i] = k; } else { p.cost[i - 1] = p.cost[i - 2]; p.split[i] = 0; }
+        }
+    }
+    void roots(int n, int j, std::vector<int>& list) const {         // the (at most j) roots plan() chose for subtree n
+        const BinNode& b = bin[size_t(n)];
+        while (j > 1 && b.left >= 0 && plans[size_t(n)].split[j] == 0) --j;
+        if (j <= 1 || b.left < 0) { list.push_back(n); return; }
+        const int k = plans[size_t(n)].split[j];
+        roots(b.left, k, list); roots(b.right, j - k, list);
+    }
+    bool is_leaf(int n) const { return bin[size_t(n)].left < 0 || (optimal && plans[size_t(n)].leaf); }
+
     // Emits the wide node for binary node `b` (an inner node); returns its index.  `pending` = stack entries
     // the device walk may hold when it enters this node (worst case: every sibling on the way was pushed).
     int emit_wide(int b, int depth, int pending) {
         wide_depth = std::max(wide_depth, depth);
-        std::vector<int> kids = {bin[size_t(b)].left, bin[size_t(b)].right};
+        std::vector<int> kids;
+        if (optimal) {
+            const int k = plans[size_t(b)].split[8];
+            roots(bin[size_t(b)].left, k, kids); roots(bin[size_t(b)].right, ptk::kWide - k, kids);
+            for (int kid : kids)                                        // (see below; a lopsided tree falls back to the greedy rule)
+                if (pending + int(kids.size()) - 1 + (is_leaf(kid) ? 0 : bin[size_t(kid)].height) > ptk::kWideStack) { kids.clear(); break; }
+        }
+        const bool planned = !kids.empty();
+        if (!planned) kids = {bin[size_t(b)].left, bin[size_t(b)].right};
         // Every child beyond the one being walked may sit on the device's traversal stack.  Invariant: pending +
         // height(subtree) <= kWideStack, where height is that of the BINARY subtree -- it holds at the root (the binary
         // depth is capped) and a node only adopts grandchildren while it keeps holding for every child, so even the most
         // lopsided tree fits the device stack: deep down the nodes simply get narrower.
-        while (int(kids.size()) < ptk::kWide) {
+        while (!planned && int(kids.size()) < ptk::kWide) {
             int pick = -1; double area = -1.0;
             for (size_t i = 0; i < kids.size(); ++i) {
                 const BinNode& k = bin[size_t(kids[i])];
-                if (k.left < 0 || !(k.box.half_area() > area)) continue;
+                if (is_leaf(kids[i]) || !(k.box.half_area() > area)) continue;
                 int tallest = std::max(bin[size_t(k.left)].height, bin[size_t(k.right)].height);
                 for (size_t q = 0; q < kids.size(); ++q) if (q != i) tallest = std::max(tallest, bin[size_t(kids[q])].height);
                 if (pending + int(kids.size()) + tallest > ptk::kWideStack) continue;          // (|kids| + 1 children -> |kids| pushed)
@@ -255,7 +310,7 @@ template <typename R> struct BvhBuilder {
             if (c < int(kids.size())) {
                 const BinNode& k = bin[size_t(kids[size_t(c)])];
                 padded<R>(k.box, lo, hi);
-                code = k.left >= 0 ? emit_wide(kids[size_t(c)], depth + 1, need) : make_leaf(k);
+                code = is_leaf(kids[size_t(c)]) ? make_leaf(k) : emit_wide(kids[size_t(c)], depth + 1, need);
             }
             const size_t at = (size_t(me) * ptk::kWide + size_t(c)) * 2;
             out.wide[at] = {lo[0], lo[1], lo[2], code_as(R(0), code)};
@@ -295,10 +350,13 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
     }
     if (prims.empty()) { m.bvh_root = -1; return; }
     BvhBuilder<R> builder{tris, out, prims};
+    if (const char* ov = std::getenv("PTC_BVH_BIN_LEAF")) builder.bin_leaf = std::max(1, std::min(ptk::kLeafTris, std::atoi(ov)));   // tuning overrides
+    if (const char* ov = std::getenv("PTC_BVH_OPTIMAL")) builder.optimal = std::atoi(ov) != 0;
     const int root = builder.build(0, int(prims.size()), 0);
+    if (builder.optimal) { builder.plans.resize(builder.bin.size()); builder.plan(root); }
     if (builder.bin[size_t(root)].height > ptk::kWideStack) fail("object %d: triangle tree is %d levels deep (limit %d)", obj_index, builder.bin[size_t(root)].height, ptk::kWideStack);
     const Box3 root_box = builder.bin[size_t(root)].box;
-    if (builder.bin[size_t(root)].left < 0) {             // a single leaf: give it a node to hang from
+    if (builder.is_leaf(root)) {                          // a single leaf: give it a node to hang from
         const int me = int(out.wide.size()) / (2 * ptk::kWide);
         out.wide.resize(out.wide.size() + 2 * ptk::kWide, ptk::V4<R>{R(0), R(0), R(0), code_as(R(0), ptk::kEmptyChild)});
         R lo[3], hi[3];
