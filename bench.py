@@ -303,8 +303,13 @@ def main():
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sm_count * 128 * 2 * sm_mhz_peak * 1e6 / 1e12
     kernel_ms_avg = sum(kern_ms) / len(kern_ms)
+    try:
+        fma_measured = T.debug_fma_peak(local_rank)           # pure-FFMA kernel on this GPU, outside every timed region
+    except Exception:
+        fma_measured = None
     roofline = {"bound": "fp32_issue", "achieved": None, "peak": fp32_peak, "unit": "TFLOP/s", "frac": None, "traffic": None,
                 "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_mhz_peak:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
+                "peak_fma_microbenchmark": fma_measured,
                 "kernel": "ptk::trace_kernel", "kernel_ms": kernel_ms_avg,
                 "hbm_algorithmic_bytes_per_launch": len(ctx.rows) * W * 40,
                 "hbm_gbs_achieved": len(ctx.rows) * W * 40 / (kernel_ms_avg / 1e3) / 1e9,

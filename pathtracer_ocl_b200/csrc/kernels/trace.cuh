@@ -953,6 +953,20 @@ __global__ void rgba8_kernel(const double4* __restrict__ in, uchar4* __restrict_
     out[i] = make_uchar4(q(c.x), q(c.y), q(c.z), 255);
 }
 
+// Calibration of the FP32 issue roofline: 8 independent FFMA chains per thread, nothing else.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ out, int iters) {
+    float a0 = threadIdx.x * 1e-6f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999999f, c = 1e-7f * (blockIdx.x + 1);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // Test hook: evaluate the RNG on the device (parity tests compare it bit for bit with the oracle).
 __global__ void noise3d_kernel(const float* __restrict__ xyz, float* __restrict__ out, int n, int mode) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

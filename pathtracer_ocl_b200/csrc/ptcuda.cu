@@ -1076,6 +1076,36 @@ int ptc_debug_noise3d(const float* xyz, int n, int rng_mode, float* out, char* e
     });
 }
 
+// Measurement hook (not part of the drop-in surface): achieved FP32 FFMA throughput of a device in TFLOP/s
+// (2 flops per FFMA), best of 5 launches of ptk::fma_peak_kernel -- calibrates the issue roofline bench.py reports against.
+int ptc_debug_fma_peak(int device, double* tflops, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!tflops) fail("ptc_debug_fma_peak: tflops is NULL");
+        if (ptc_device_count() <= 0) fail("no usable CUDA device; libptcuda has no CPU fallback");
+        CUDA_OK(cudaSetDevice(device));
+        int sms = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const int blocks = sms * 8, threads = 256, iters = 4096;
+        float* out = nullptr;
+        CUDA_OK(cudaMalloc(&out, size_t(blocks) * threads * sizeof(float)));
+        cudaEvent_t e0, e1;
+        CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; ++rep) {                       // first launch = warm-up
+            CUDA_OK(cudaEventRecord(e0));
+            ptk::fma_peak_kernel<<<blocks, threads>>>(out, iters);
+            CUDA_OK(cudaEventRecord(e1));
+            CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+        CUDA_OK(cudaGetLastError());
+        *tflops = 2.0 * 8 * 16 * double(iters) * blocks * threads / (best * 1e-3) / 1e12;
+    });
+}
+
 // Test hook (not part of the drop-in surface; host only, no device needed): flattens the job's scene in
 // double and copies one array of the rebuilt mesh index out, so tests can check the builder's invariants
 // (every triangle in exactly one leaf, child boxes containing their triangles, depth) and replay the walk.

@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
         L.ptc_read_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         L.ptc_debug_mesh_index.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_char_p, C.c_int]
         L.ptc_debug_mesh_index.restype = C.c_int64
+        L.ptc_debug_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -317,6 +318,15 @@ def debug_noise3d(xyz: np.ndarray, rng_mode: int = RNG_PARITY) -> np.ndarray:
     if lib().ptc_debug_noise3d(a.ctypes.data, a.shape[0], rng_mode, out.ctypes.data, err, 512) != 0:
         raise PtcError(err.value.decode())
     return out
+
+
+def debug_fma_peak(device: int = 0) -> float:
+    """Measurement hook: achieved FP32 FFMA throughput of `device` in TFLOP/s (a pure-FFMA kernel, best of 5)."""
+    out = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    if lib().ptc_debug_fma_peak(int(device), C.byref(out), err, 512) != 0:
+        raise PtcError(err.value.decode())
+    return float(out.value)
 
 
 _MESH_INDEX_ARRAYS = {  # name -> (selector, dtype, trailing shape)

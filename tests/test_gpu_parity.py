@@ -36,6 +36,13 @@ def test_device_is_a_b200_class_gpu():
     assert devs and devs[0].startswith("Index: 0 Type: GPU Name: ")
 
 
+def test_fma_microbenchmark_calibrates_the_issue_roofline():
+    """The pure-FFMA kernel must land near 148 SMs x 128 lanes x 2 x f_SM (74.4 TFLOP/s at 1965 MHz): it is the
+    measured counterpart of the nominal peak bench.py divides by."""
+    tflops = T.debug_fma_peak(0)
+    assert 40.0 < tflops < 80.0, tflops
+
+
 def test_rng_stream_is_bit_identical_to_the_oracle():
     rng = np.random.default_rng(1)
     xyz = np.concatenate([(rng.random((300000, 3)) * [1, 4096, 4096]), (rng.random((100000, 3)) * [1, 4096 ** 2, 10]),
