@@ -37,10 +37,12 @@
 
 namespace ptk {
 
-// Resident-blocks hints for the register allocator, tuned by measurement on B200 (profiles/):
-// fp32 runs best at 6 blocks x 128 threads (72 registers), fp64 needs more registers per thread.
+// Resident-blocks hints for the register allocator, tuned by measurement on B200 (profiles/): the fp32 kernels run
+// best at 8 blocks x 128 threads (64 registers; reference scene 10.90 / 10.91 / 11.25 / 11.26 Gpaths/s at 5 / 6 / 7 / 8
+// blocks -- the analytic kernel fits 64 registers with 8 bytes of spill), fp64 needs more registers per thread
+// (3 / 5 / 6 blocks: 4.76 / 4.78 / 4.42 Gpaths/s).
 #ifndef PTK_MIN_BLOCKS
-#define PTK_MIN_BLOCKS 6
+#define PTK_MIN_BLOCKS 8
 #endif
 #ifndef PTK_MIN_BLOCKS_F64
 #define PTK_MIN_BLOCKS_F64 3
