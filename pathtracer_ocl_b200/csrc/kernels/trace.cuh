@@ -20,10 +20,12 @@
 //     matrix entries are read through the uniform datapath and feed FFMA directly instead of
 //     costing load instructions and registers (the reference copies 16 KB of 1024-byte records
 //     into __local per work-item, tracer.cl:846-849); material data is fetched per hit;
-//   * the BVH is re-emitted in traversal (pre-)order with skip links, so the walk needs no stack
-//     and visits exactly the nodes, in exactly the order, of the reference's stack walk
-//     (tracer.cl:624-714); nodes and triangles are 16-byte-vectorised records (48 B of test data
-//     per triangle instead of a 512-byte stride);
+//   * mesh objects are re-indexed on the host by an 8-wide SAH BVH over the caller's own triangle
+//     records, walked cooperatively -- eight lanes share one ray, four rays per warp -- and every
+//     candidate hit is checked against the caller's BVH boxes so that exactly the triangles the
+//     reference's stack walk (tracer.cl:624-714) would have tested can win (see "mesh objects"
+//     below); nodes and triangles are 16-byte-vectorised records (48 B of test data per triangle
+//     instead of a 512-byte stride);
 //   * the depth-of-field lens points depend only on the sample index, so they come from a table
 //     built once on the host instead of two sqrt, a divide and a sincos per path;
 //   * everything is templated on the arithmetic type: float = "fp32 mode", double = tracer.cl.
@@ -119,9 +121,9 @@ template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { retu
 // kernel parameter block (constant bank, uniform loads).
 template <typename R> struct alignas(16) DObjHot {
     R inv[12];          // rows 0..2 of `inverse` (tracer.cl:547-548)
-    R aux[6];           // cylinder: min_y, max_y; group: bb_min.xyz, bb_max.xyz
+    R aux[6];           // cylinder: min_y, max_y; group: the object's own AABB bb_min.xyz, bb_max.xyz (tracer.cl:609)
     int type;           // 0 plane 1 sphere 2 cylinder 3 cube 4 group, anything else: never hit
-    int node_begin, node_end;   // group: range of BVH nodes (all root children, in root order)
+    int node_begin, node_end;   // group: its range in the re-emitted reference nodes (node_lo / node_hi / node_parent)
     int pad;
 };
 // "Shade" half: read once per hit, indexed by the (lane-varying) hit object; lives in global memory.
