@@ -42,12 +42,15 @@ namespace ptk {
 // Resident-blocks hints for the register allocator, tuned by measurement on B200 (profiles/): the fp32 kernels run
 // best at 8 blocks x 128 threads (64 registers; reference scene 10.90 / 10.91 / 11.25 / 11.26 Gpaths/s at 5 / 6 / 7 / 8
 // blocks -- the analytic kernel fits 64 registers with 8 bytes of spill), fp64 needs more registers per thread
-// (3 / 5 / 6 blocks: 4.76 / 4.78 / 4.42 Gpaths/s).
+// (analytic kernel at 3 / 4 / 5 blocks: 4.64 / 4.69 / 5.03 Gpaths/s; mesh kernel, teapot: 0.78 / 0.88 / 0.79).
 #ifndef PTK_MIN_BLOCKS
 #define PTK_MIN_BLOCKS 8
 #endif
 #ifndef PTK_MIN_BLOCKS_F64
-#define PTK_MIN_BLOCKS_F64 3
+#define PTK_MIN_BLOCKS_F64 5
+#endif
+#ifndef PTK_MESH_MIN_BLOCKS_F64
+#define PTK_MESH_MIN_BLOCKS_F64 4
 #endif
 #ifndef PTK_MESH_MIN_BLOCKS
 #define PTK_MESH_MIN_BLOCKS 8
@@ -452,10 +455,10 @@ __device__ __forceinline__ int group_min(int v) {
     v = min(v, __shfl_xor_sync(kFullMask, v, 1)); v = min(v, __shfl_xor_sync(kFullMask, v, 2)); return min(v, __shfl_xor_sync(kFullMask, v, 4));
 }
 
-// One mesh object against the rays of the lanes with `want` set.  Called by all 32 lanes.  `po`, `pd`:
-// this lane's ray in the object's space.  `stk`: this lane's GROUP's stack in shared memory.
+// One mesh object against the rays of the lanes with `want` set.  Called by all 32 lanes.  `ro`, `rd`:
+// this lane's ray in world space.  `stk`: this lane's GROUP's stack in shared memory.
 template <typename R>
-__device__ __forceinline__ void mesh_hit(const Params<R>& P, const DMesh<R>& m, int j, V3<R> po, V3<R> pd, bool want, int lane, Hit<R>& h, int2* __restrict__ stk) {
+__device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& ob, const DMesh<R>& m, int j, V3<R> ro, V3<R> rd, bool want, int lane, Hit<R>& h, int2* __restrict__ stk) {
     const R eps = P.eps;
     const int sub = lane & 7, gbase = lane & 24, grp = lane >> 3;
     constexpr int kDone = 0x7fffffff;
@@ -468,7 +471,9 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DMesh<R>& m, 
         const int owner = active ? __ffs(mine_bits) - 1 : lane;
         const unsigned round_bits = todo ^ (t3 & (t3 - 1));
         todo = t3 & (t3 - 1);
-        const V3<R> o = shfl3(po, owner), d = shfl3(pd, owner);
+        // the owner's ray, taken from its world-space registers and moved to the object's space here (the matrix is a
+        // uniform constant-bank operand): cheaper than keeping every lane's object-space ray alive across the rounds
+        const V3<R> o = xf_point(ob.inv, shfl3(ro, owner)), d = xf_dir(ob.inv, shfl3(rd, owner));
         R ct = __shfl_sync(kFullMask, h.t, owner);
         const int cobj = __shfl_sync(kFullMask, h.obj, owner);
         const IDir<R> k = inv_dir(d);
@@ -592,7 +597,7 @@ __device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R>
             const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);
             const bool want = live && finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1) &&
                               keep_box(o, inv_dir(d), m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], h.t * R(1.0001), tn);
-            mesh_hit<R>(P, m, j, o, d, want, lane, h, stk);
+            mesh_hit<R>(P, ob, m, j, ro, rd, want, lane, h, stk);
         }
     }
 }
@@ -859,7 +864,7 @@ template <typename R> __device__ __forceinline__ void store_pixel(const Params<R
 // GROUPS = the scene contains mesh objects: only then is the cooperative BVH walk (and its shared-memory
 // stacks) compiled in.
 template <typename R, int RNG, bool GROUPS>
-__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCKS_F64 : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
+__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS_F64) : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
     __shared__ int2 mesh_stacks[GROUPS ? kBlockThreads / kWide : 1][GROUPS ? kWideStack + 1 : 1];   // one per 8-lane group
     const PixelSlot px = pixel_slot(P);
     const int lane = threadIdx.x & 31;
@@ -872,7 +877,10 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     const R fx = R(px.lx), fy = R(px.gy);
     const V3<R> cam_origin = {P.cam.inv[3], P.cam.inv[7], P.cam.inv[11]};   // inverse * (0,0,0,1)
 
-    double col_r = 0.0, col_g = 0.0, col_b = 0.0;
+    // per-pixel radiance sums (tracer.cl:1179) live in shared memory: touched once per finished path, they would
+    // otherwise hold six registers for the whole life of the thread
+    __shared__ double col_sum[3][kBlockThreads];
+    col_sum[0][threadIdx.x] = 0.0; col_sum[1][threadIdx.x] = 0.0; col_sum[2][threadIdx.x] = 0.0;
     Path<R> s;
     s.n = (unsigned)(P.sample_begin + slice);
     const unsigned n_end = (unsigned)P.sample_end;      // == samples unless a caller renders a sample range
@@ -888,7 +896,7 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
     // its next one too, so the (RNG-heavy) generation code executes with most lanes active instead
     // of with the ~quarter of the lanes whose path happened to end on this iteration.  The RNG is a
     // pure function of (seed, sample, bounce), so evaluation order does not change any value.
-    V3<R> nxo = cam_origin, nxd = {R(0), R(0), R(0)};
+    __shared__ R next_ray[6][kBlockThreads];          // the parked ray: written once and read once per path, so not in registers
     bool have_next = false;
 
     while (true) {
@@ -898,12 +906,17 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
         if (__any_sync(kFullMask, starved)) {
             const unsigned gn = fresh ? s.n : s.n + (unsigned)P.slices;    // the sample this lane will start next
             if (live && !have_next && gn < n_end) {
+                V3<R> nxo, nxd;
                 camera_ray<R, RNG>(P, fx, fy, fgi, fgi2, gn, cam_origin, nxo, nxd);
+                next_ray[0][threadIdx.x] = nxo.x; next_ray[1][threadIdx.x] = nxo.y; next_ray[2][threadIdx.x] = nxo.z;
+                next_ray[3][threadIdx.x] = nxd.x; next_ray[4][threadIdx.x] = nxd.y; next_ray[5][threadIdx.x] = nxd.z;
                 have_next = true;
             }
         }
         if (fresh && live) {
-            s.ro = nxo; s.rd = nxd; have_next = false;
+            s.ro = {next_ray[0][threadIdx.x], next_ray[1][threadIdx.x], next_ray[2][threadIdx.x]};
+            s.rd = {next_ray[3][threadIdx.x], next_ray[4][threadIdx.x], next_ray[5][threadIdx.x]};
+            have_next = false;
             s.b = 0; s.effective = 0; s.inside = false;
             s.mask = {R(1), R(1), R(1)}; s.accum = {R(0), R(0), R(0)};
             fresh = false;
@@ -916,12 +929,13 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? PTK_MIN_BLOCK
         bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
         if (live && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);
         if (done) {
-            col_r += (double)s.accum.x; col_g += (double)s.accum.y; col_b += (double)s.accum.z;   // tracer.cl:1179
+            col_sum[0][threadIdx.x] += (double)s.accum.x; col_sum[1][threadIdx.x] += (double)s.accum.y;   // tracer.cl:1179
+            col_sum[2][threadIdx.x] += (double)s.accum.z;
             s.n += (unsigned)P.slices;
             fresh = true;
         }
     }
-    if (px.has_pixel) store_pixel(P, px, slice, col_r, col_g, col_b);
+    if (px.has_pixel) store_pixel(P, px, slice, col_sum[0][threadIdx.x], col_sum[1][threadIdx.x], col_sum[2][threadIdx.x]);
 }
 
 // Sums the per-slice partials in slice order (deterministic) and applies the 1/samples weight.

@@ -118,7 +118,8 @@ def test_against_committed_golden_fixtures(path):
 
 
 @pytest.mark.parametrize("name,W,H,ap,fl", [("reference", 96, 72, 0.15, 1.6), ("teapot", 64, 48, 0.0, 0.0),
-                                            ("transparency", 64, 48, 0.0, 0.0), ("textures", 64, 48, 0.0, 0.0)])
+                                            ("transparency", 64, 48, 0.0, 0.0), ("textures", 64, 48, 0.0, 0.0),
+                                            ("gopher", 64, 48, 0.0, 0.0), ("cubemap", 48, 36, 0.0, 0.0)])
 def test_converged_1024spp_rmse(name, W, H, ap, fl):
     spp = 1024
     sc = S.build_scene(name, W, H, ap, fl, tex_scale=16)
