@@ -162,21 +162,25 @@ template <typename R> struct BvhBuilder {
         const double ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
         if (depth < kSahDepth && (ext[0] > 0 || ext[1] > 0 || ext[2] > 0)) {
             double best = 1e300; int best_axis = -1, best_bin = -1;
+            Box3 bb[3][kBins]; int bn[3][kBins] = {};
+            double scale3[3];
+            for (int a = 0; a < 3; ++a) scale3[a] = ext[a] > 0 ? double(kBins) / ext[a] : 0.0;
+            for (int i = begin; i < end; ++i) {                    // one pass bins the three axes
+                const BuildPrim& p = prims[size_t(i)];
+                for (int a = 0; a < 3; ++a) {
+                    int k = int((p.c[a] - cb.lo[a]) * scale3[a]);
+                    k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                    bb[a][k].merge(p.box); bn[a][k]++;
+                }
+            }
             for (int a = 0; a < 3; ++a) {
                 if (!(ext[a] > 0)) continue;
-                Box3 bb[kBins]; int bn[kBins] = {0};
-                const double scale = double(kBins) / ext[a];
-                for (int i = begin; i < end; ++i) {
-                    int k = int((prims[size_t(i)].c[a] - cb.lo[a]) * scale);
-                    k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-                    bb[k].merge(prims[size_t(i)].box); bn[k]++;
-                }
                 double right_area[kBins]; int right_n[kBins];
                 Box3 acc; int n = 0;
-                for (int k = kBins - 1; k > 0; --k) { acc.merge(bb[k]); n += bn[k]; right_area[k] = acc.half_area(); right_n[k] = n; }
+                for (int k = kBins - 1; k > 0; --k) { acc.merge(bb[a][k]); n += bn[a][k]; right_area[k] = acc.half_area(); right_n[k] = n; }
                 acc = Box3(); n = 0;
                 for (int k = 0; k < kBins - 1; ++k) {
-                    acc.merge(bb[k]); n += bn[k];
+                    acc.merge(bb[a][k]); n += bn[a][k];
                     if (n == 0 || right_n[k + 1] == 0) continue;
                     // a leaf costs one cooperative step per started group of bin_leaf triangles
                     const double cost = acc.half_area() * std::ceil(n / double(bin_leaf)) + right_area[k + 1] * std::ceil(right_n[k + 1] / double(bin_leaf));
@@ -326,6 +330,7 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
                 ptk::DMesh<R>& m) {
     std::vector<RefTri> list;
     bool nested = true;
+    const auto t_begin = Clock::now();
     for (int c = 0; c < s.child_count; ++c) collect_reference_nodes<R>(groups, n_groups, n_tris, s.children[c], -1, 0, out, list, nested);
     m.flags = nested ? 1 : 0;
     std::vector<BuildPrim> prims;
@@ -350,10 +355,17 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
     }
     if (prims.empty()) { m.bvh_root = -1; return; }
     BvhBuilder<R> builder{tris, out, prims};
+    builder.bin.reserve(prims.size());
+    out.tri_test.reserve(out.tri_test.size() + 3 * prims.size()); out.tri_shade.reserve(out.tri_shade.size() + 3 * prims.size());
+    out.tri_info.reserve(out.tri_info.size() + prims.size());
+    out.wide.reserve(out.wide.size() + prims.size() * 2);
     if (const char* ov = std::getenv("PTC_BVH_BIN_LEAF")) builder.bin_leaf = std::max(1, std::min(ptk::kLeafTris, std::atoi(ov)));   // tuning overrides
     if (const char* ov = std::getenv("PTC_BVH_OPTIMAL")) builder.optimal = std::atoi(ov) != 0;
+    const auto t_prims = Clock::now();
     const int root = builder.build(0, int(prims.size()), 0);
+    const auto t_built = Clock::now();
     if (builder.optimal) { builder.plans.resize(builder.bin.size()); builder.plan(root); }
+    const auto t_planned = Clock::now();
     if (builder.bin[size_t(root)].height > ptk::kWideStack) fail("object %d: triangle tree is %d levels deep (limit %d)", obj_index, builder.bin[size_t(root)].height, ptk::kWideStack);
     const Box3 root_box = builder.bin[size_t(root)].box;
     if (builder.is_leaf(root)) {                          // a single leaf: give it a node to hang from
@@ -373,6 +385,11 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
     R lo[3], hi[3];
     padded<R>(root_box, lo, hi);
     for (int a = 0; a < 3; ++a) { m.root_lo[a] = lo[a]; m.root_hi[a] = hi[a]; }
+    if (std::getenv("PTC_DEBUG_TIMING")) {
+        auto ms = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[build_mesh] object %d: %zu triangles; reference nodes + boxes %.2f ms, binary SAH %.2f ms, plan %.2f ms, emit %.2f ms\n",
+                     obj_index, prims.size(), ms(t_begin, t_prims), ms(t_prims, t_built), ms(t_built, t_planned), ms(t_planned, Clock::now()));
+    }
 }
 
 template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
