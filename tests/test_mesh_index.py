@@ -353,3 +353,43 @@ def test_degenerate_mesh_stays_within_the_device_stack(n, ratio):
     stats = {"nodes": 0, "leaves": 0}
     for i, (o, d) in enumerate(rays_for(m, obj_lo, obj_hi, rng, 120)):
         assert replayed_winner(m, m["mesh"][obj], obj_lo, obj_hi, o, d, 1024.0, stats) == reference_winner(m, obj_lo, obj_hi, o, d, 1024.0)
+
+
+def test_non_finite_triangles_are_left_out_of_the_index():
+    """A triangle with a NaN / infinite coordinate can never be recorded with EPSILON < t < 1024 upstream (every product
+    of its test is NaN, inf or 0), so the builder drops it instead of poisoning the boxes; the others stay reachable."""
+    sc = S.build_scene("teapot", 32, 24)
+    tris = sc.triangles.copy()
+    tv = tris.view(S.TRIANGLE_DTYPE)
+    bad = [5, 77, 1000, 6319]
+    tv["p1"][bad[0]][0] = np.nan
+    tv["e1"][bad[1]][1] = np.inf
+    tv["e2"][bad[2]][2] = -np.inf
+    tv["p1"][bad[3]][1] = np.nan
+    broken = S.SceneBuffers("teapot-nan", 32, 24, sc.objects, tris, sc.groups, sc.camera)
+    m, obj = index_of(broken)
+    assert m["tri_info"].shape[0] == sc.n_triangles - len(bad)
+    assert np.isfinite(m["tri_test"]).all() and np.isfinite(m["wide"][:, :3]).all() and np.isfinite(m["mesh"][obj, :6]).all()
+    seen = np.zeros(m["tri_info"].shape[0], dtype=bool)
+    subtree(m, int(m["mesh"][obj, 6]), 0, 0, seen, {"depth": 0, "stack": 0})
+    assert seen.all()
+    kept = set(m["tri_info"][:, 0].tolist())                    # ranks keep the reference's numbering, with gaps
+    assert len(set(range(sc.n_triangles)) - kept) == len(bad)
+
+
+def test_two_mesh_objects_get_separate_roots_over_shared_triangles():
+    sc = S.build_scene("teapot", 32, 24)
+    ov = sc.objects_view()
+    recs = np.zeros(3, dtype=S.OBJECT_DTYPE)
+    recs[0], recs[1], recs[2] = ov[0], ov[6], ov[6]
+    two = S.SceneBuffers("two", 32, 24, recs.view(np.uint8).reshape(-1), sc.triangles, sc.groups, sc.camera)
+    m = T.debug_mesh_index(two)
+    roots = m["mesh"][:, 6].astype(int)
+    assert roots[0] == -1 and roots[1] >= 0 and roots[2] > roots[1]
+    n = sc.n_triangles
+    assert m["tri_info"].shape[0] == 2 * n                      # each object owns its own slots
+    r1, r2 = m["node_range"][1], m["node_range"][2]
+    assert r1[1] - r1[0] == r2[1] - r2[0] and r2[0] == r1[1] and r1[1] - r1[0] <= sc.n_groups
+    # ranks restart per object; reference nodes of the second object point into its own node range
+    assert sorted(m["tri_info"][:n, 0].tolist()) == sorted(m["tri_info"][n:, 0].tolist()) == list(range(n))
+    assert m["tri_info"][:n, 1].max() < r1[1] <= m["tri_info"][n:, 1].min()
