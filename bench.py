@@ -62,21 +62,38 @@ def workload_name(a):
             else f"{a.scene} scene {a.width}x{a.height}@{a.samples}spp aperture={a.aperture:g} focal={a.focal_length:g}")
 
 
-# ---- CPU arm (oracle; allowed here as the timed baseline only) ------------------------------------------
-def cpu_sample(a, scene, seeds, target_s, threads):
-    """Time the oracle on the workload's frame at a reduced sample count (~target_s of CPU work)."""
+# ---- CPU arm (oracle/ is allowed here as the timed baseline only) ----------------------------------------
+# Two CPU implementations of the path exist: oracle/_ref -- the reference's OWN kernel source (tracer.cl) compiled for
+# the host through oracle/cl_shim.hpp, kind "reference" -- and the oracle, a restatement of it (kind "port") that also
+# counts events for the cost model.  The tests hold them bit-identical (tests/test_oracle_vs_reference.py).
+def cpu_kernel():
+    """(trace function, kind, note) of the CPU implementation to time: the compiled reference kernel when it is there."""
     from oracle import oracle as O
+    if O.ref_lib() is not None:
+        return (lambda scene, seeds, spp, threads: O.ref_trace(scene, seeds, spp, nthreads=threads), "reference",
+                "the reference's own kernel source (internal/ocl/tracer.cl) compiled for the host CPU through oracle/cl_shim.hpp, "
+                "work-items spread over all host threads; no OpenCL runtime exists in this image")
+    return (lambda scene, seeds, spp, threads: O.trace(scene, seeds, spp, precision=1, nthreads=threads), "port",
+            "CPU restatement of tracer.cl (oracle); the compiled reference kernel (oracle/_ref) is not present")
+
+
+def cpu_sample(a, scene, seeds, target_s, threads):
+    """Time the CPU implementation on the workload's frame at a reduced sample count (~target_s of CPU work); the event
+    counters of the cost model come from the oracle on the same sample."""
+    from oracle import oracle as O
+    run, kind, note = cpu_kernel()
     px = a.width * a.height
     t0 = time.perf_counter()
-    _, cnt = O.trace(scene, seeds, 1, precision=1, nthreads=threads)
+    run(scene, seeds, 1, threads)
     t1 = time.perf_counter() - t0
     spp = int(max(2, min(a.samples, target_s / max(t1, 1e-3))))
     t0 = time.perf_counter()
-    _, cnt = O.trace(scene, seeds, spp, precision=1, nthreads=threads)
+    run(scene, seeds, spp, threads)
     dt = time.perf_counter() - t0
+    _, cnt = O.trace(scene, seeds, max(2, spp // 4) if kind == "reference" else spp, precision=1, nthreads=threads)
     flops = O.model_flops(cnt, dof=a.aperture != 0.0)
     return dict(spp=spp, seconds=dt, mpaths=px * spp / dt / 1e6, flops_per_path=flops / cnt["paths"],
-                segments_per_path=cnt["segments"] / cnt["paths"])
+                segments_per_path=cnt["segments"] / cnt["paths"], kind=kind, note=note)
 
 
 def run_reference(a):
@@ -84,22 +101,22 @@ def run_reference(a):
     if rank != 0:
         return 0
     from pathtracer_ocl_b200 import scene as S
-    from oracle import oracle as O
+    run, kind, note = cpu_kernel()
     threads = os.cpu_count() or 1
     scene = S.build_scene(a.scene, a.width, a.height, a.aperture, a.focal_length)
     seeds = S.make_seeds(0x5EED0002, a.width * a.height)
     px = a.width * a.height
     budget = min(10.0, 150.0 / max(1, a.steps + a.warmup))
     t0 = time.perf_counter()
-    O.trace(scene, seeds, 1, precision=1, nthreads=threads)
+    run(scene, seeds, 1, threads)
     t1 = time.perf_counter() - t0
     spp = int(max(1, min(a.samples, budget / max(t1, 1e-3))))
     for _ in range(a.warmup):
-        O.trace(scene, seeds, spp, precision=1, nthreads=threads)
+        run(scene, seeds, spp, threads)
     times = []
     for _ in range(a.steps):
         t0 = time.perf_counter()
-        O.trace(scene, seeds, spp, precision=1, nthreads=threads)
+        run(scene, seeds, spp, threads)
         times.append(time.perf_counter() - t0)
     total = sum(times)
     value = px * spp * a.steps / total / 1e6
@@ -109,8 +126,7 @@ def run_reference(a):
         "warmup": a.warmup, "ms_per_step": total / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "CPU restatement of tracer.cl (oracle); the Go/OpenCL reference cannot run in this image"},
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": kind, "sample": sample, "note": note},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "extrapolated_full_config_wall_s": px * a.samples / (value * 1e6),
     }
@@ -290,7 +306,7 @@ def main():
         threads = os.cpu_count() or 1
         cs = cpu_sample(a, scene, seeds, a.cpu_seconds, threads)
         flops_per_path = cs["flops_per_path"]
-        cpu = {"value": cs["mpaths"], "unit": "Mpaths/s", "cores": threads, "kind": "port",
+        cpu = {"value": cs["mpaths"], "unit": "Mpaths/s", "cores": threads, "kind": cs["kind"], "note": cs["note"],
                "sample": f"{W}x{H} frame at {cs['spp']} of {spp} spp, {cs['seconds']:.1f} s (cost is linear in spp)",
                "extrapolated_full_config_wall_s": total_paths / (cs["mpaths"] * 1e6),
                "segments_per_path": cs["segments_per_path"]}

@@ -110,3 +110,58 @@ def model_flops(counters: Dict[str, int], dof: bool = False) -> float:
     if dof:
         f += 30.0 * counters.get("paths", 0)
     return f
+
+
+# ---- the reference's own kernel, compiled for the CPU (oracle/build_ref.py) -----------------------------------------
+_ref_lib = None
+
+
+def ref_lib() -> Optional[C.CDLL]:
+    """oracle/_ref/libtracer_ref.so: /root/reference/internal/ocl/tracer.cl compiled as C++ through cl_shim.hpp.
+    Built here when the reference source is present; elsewhere (the GPU box) the prebuilt library is used; None if
+    neither exists."""
+    global _ref_lib
+    if _ref_lib is None:
+        from . import build_ref
+        path = build_ref.build()
+        if not path:
+            return None
+        L = C.CDLL(path)
+        L.ref_trace.restype = C.c_int
+        L.ref_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_void_p]
+        _ref_lib = L
+    return _ref_lib
+
+
+def ref_trace(scene, seeds: np.ndarray, samples: int, rows: Optional[Tuple[int, int]] = None,
+              nthreads: Optional[int] = None) -> np.ndarray:
+    """Rows [rows[0], rows[1]) of `scene` rendered by the REFERENCE kernel itself (fp64, canonical sin).  [nrows, W, 4]."""
+    L = ref_lib()
+    if L is None:
+        raise RuntimeError("the compiled reference kernel is not available (no /root/reference and no oracle/_ref/libtracer_ref.so)")
+    W, H = scene.width, scene.height
+    seeds = np.ascontiguousarray(seeds, dtype=np.float64)
+    assert seeds.size == W * H, "one seed per pixel"
+    r0, r1 = rows if rows is not None else (0, H)
+    if nthreads is None:
+        nthreads = os.cpu_count() or 1
+    out = np.zeros(((r1 - r0), W, 4), dtype=np.float64)
+    ptrs = (C.c_void_p * 3)()
+    tw, th, tl = (C.c_int32 * 3)(), (C.c_int32 * 3)(), (C.c_int32 * 3)()
+    keep = []
+    for c in range(3):
+        t = scene.textures[c]
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=np.uint8)
+            keep.append(t)
+            ptrs[c] = t.ctypes.data
+            tl[c], th[c], tw[c] = t.shape[0], t.shape[1], t.shape[2]
+    rc = L.ref_trace(scene.objects.ctypes.data, scene.n_objects,
+                     scene.triangles.ctypes.data if scene.n_triangles else None, scene.n_triangles,
+                     scene.groups.ctypes.data if scene.n_groups else None, scene.n_groups,
+                     scene.camera.ctypes.data, ptrs, tw, th, tl, seeds.ctypes.data, samples, r0, r1, nthreads, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"ref_trace failed with code {rc}")
+    return out

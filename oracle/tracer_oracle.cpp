@@ -6,12 +6,14 @@
 // load this library, and only as the checker / the timed CPU baseline.  The product (libptcuda)
 // never links or calls it.
 //
-// PARITY UNPINNED at kernel level: the reference has no golden kernel outputs (its only kernel test,
-// internal/app/tracer/renderer_test.go:11-19, asserts nothing) and neither Go nor an OpenCL runtime
-// exists in this image, so the reference itself cannot be run.  What IS pinned, by the reference's
-// own unit-test vectors replayed in tests/test_oracle_golden.py: the ray/AABB slab test
-// (shapes/boundingbox_test.go:203-262), spherical UVs (shapes/sphericalmap_test.go:16-23), cube-face
-// selection and cube-map lookups (shapes/cubemap_test.go:9-165).
+// PINNED on the reference kernel itself: tests/test_oracle_vs_reference.py renders every scene with this file AND with
+// the reference's own kernel source (internal/ocl/tracer.cl compiled for the host CPU through cl_shim.hpp, see
+// build_ref.py) on the same records and seeds and requires bit-identical pixels (fp64; both use the canonical float
+// sin() of canon_rng.h -- OpenCL leaves sin's accuracy and FMA contraction to the implementation).  What cannot be
+// pinned: the Go host side and a real OpenCL runtime (neither exists in this image), and the fp32 mode / fast RNG
+// stream, which the reference does not have.  The reference's own unit-test vectors are replayed in
+// tests/test_oracle_golden.py: the ray/AABB slab test (shapes/boundingbox_test.go:203-262), spherical UVs
+// (shapes/sphericalmap_test.go:16-23), cube-face selection and cube-map lookups (shapes/cubemap_test.go:9-165).
 //
 // Structure follows the kernel line by line (same loop nest, same 4-wide vector arithmetic, same
 // quirks); `Real` is double for the tracer.cl semantics and float for the "fp32 mode".  Variables
