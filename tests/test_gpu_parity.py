@@ -91,6 +91,21 @@ def test_low_spp_pixel_parity(name, W, H, spp, ap, fl, precision):
     assert frac >= 0.999, f"{frac * 100:.3f}% of pixels within {TOL[precision]:g} (worst {worst:.3e})"
 
 
+@pytest.mark.skipif(O.ref_lib() is None, reason="no prebuilt oracle/_ref/libtracer_ref.so")
+@pytest.mark.parametrize("name,W,H,spp,ap,fl", [("reference", 128, 96, 1, 0.15, 1.6), ("teapot", 96, 72, 1, 0.0, 0.0),
+                                                ("transparency", 96, 72, 2, 0.0, 0.0), ("textures", 96, 72, 2, 0.0, 0.0)])
+def test_pixel_parity_against_the_reference_kernel_itself(name, W, H, spp, ap, fl):
+    """The CUDA path against the reference's own tracer.cl, compiled for the CPU (oracle/_ref; the oracle is held
+    bit-identical to it by tests/test_oracle_vs_reference.py): the BASELINE gates, 1e-6 in fp64 mode and 1e-3 in fp32."""
+    sc = S.build_scene(name, W, H, ap, fl, tex_scale=16)
+    seeds = S.make_seeds(0xCE11 + W, W * H)
+    ref = O.ref_trace(sc, seeds, spp)
+    for precision in (T.FP64, T.FP32):
+        img = T.render_scene(sc, spp, seeds, precision=precision)
+        frac, worst = frac_within(img, ref, TOL[precision])
+        assert frac >= 0.999, f"precision {precision}: {frac * 100:.3f}% of pixels within {TOL[precision]:g} (worst {worst:.3e})"
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name,W,H,spp,ap,fl", [("reference", 128, 96, 1, 0.15, 1.6), ("transparency", 96, 72, 2, 0.0, 0.0),
                                                 ("gopher", 96, 72, 1, 0.0, 0.0), ("textures", 64, 48, 2, 0.0, 0.0)])
