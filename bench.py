@@ -66,10 +66,13 @@ def workload_name(a):
 # Two CPU implementations of the path exist: oracle/_ref -- the reference's OWN kernel source (tracer.cl) compiled for
 # the host through oracle/cl_shim.hpp, kind "reference" -- and the oracle, a restatement of it (kind "port") that also
 # counts events for the cost model.  The tests hold them bit-identical (tests/test_oracle_vs_reference.py).
-def cpu_kernel():
-    """(trace function, kind, note) of the CPU implementation to time: the compiled reference kernel when it is there."""
+def cpu_kernel(scene, seeds, threads):
+    """(trace function, kind, note) of the CPU implementation to time: the compiled reference kernel when it is there --
+    and when the scene stays inside the kernel's fixed 64-entry intersection arrays (tracer.cl:96-102), which the
+    reference overflows silently and a CPU build would turn into memory corruption."""
     from oracle import oracle as O
-    if O.ref_lib() is not None:
+    fits = O.trace(scene, seeds, 1, precision=1, nthreads=threads)[1]["max_intersections"] <= 60
+    if fits and O.ref_lib() is not None:
         return (lambda scene, seeds, spp, threads: O.ref_trace(scene, seeds, spp, nthreads=threads), "reference",
                 "the reference's own kernel source (internal/ocl/tracer.cl) compiled for the host CPU through oracle/cl_shim.hpp, "
                 "work-items spread over all host threads; no OpenCL runtime exists in this image")
@@ -81,7 +84,7 @@ def cpu_sample(a, scene, seeds, target_s, threads):
     """Time the CPU implementation on the workload's frame at a reduced sample count (~target_s of CPU work); the event
     counters of the cost model come from the oracle on the same sample."""
     from oracle import oracle as O
-    run, kind, note = cpu_kernel()
+    run, kind, note = cpu_kernel(scene, seeds, threads)
     px = a.width * a.height
     t0 = time.perf_counter()
     run(scene, seeds, 1, threads)
@@ -101,10 +104,10 @@ def run_reference(a):
     if rank != 0:
         return 0
     from pathtracer_ocl_b200 import scene as S
-    run, kind, note = cpu_kernel()
     threads = os.cpu_count() or 1
     scene = S.build_scene(a.scene, a.width, a.height, a.aperture, a.focal_length)
     seeds = S.make_seeds(0x5EED0002, a.width * a.height)
+    run, kind, note = cpu_kernel(scene, seeds, threads)
     px = a.width * a.height
     budget = min(10.0, 150.0 / max(1, a.steps + a.warmup))
     t0 = time.perf_counter()
