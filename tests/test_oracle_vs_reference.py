@@ -69,3 +69,17 @@ def test_the_only_edit_to_the_reference_source_is_the_vector_literal_spelling():
     # undoing the rewrite gives the source back, character for character
     assert re.sub(r"mk_(double4|double2|float4)\(", lambda m: f"({m.group(1)})(", out) == re.sub(r"\((double4|double2|float4)\)\s*\(", lambda m: f"({m.group(1)})(", src)
     assert "mk_" not in src
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(p for p in os.listdir(GOLDEN) if p.endswith(".npz")))
+def test_committed_golden_fixtures_are_the_reference_kernels_output(path):
+    """tests/golden/*.npz were written by the oracle (tools/make_golden.py); the reference kernel reproduces every one
+    of them bit for bit, so the GPU tests that read them compare against outputs of the reference itself."""
+    g = np.load(os.path.join(GOLDEN, path))
+    w, h, spp = int(g["width"]), int(g["height"]), int(g["spp"])
+    sc = S.build_scene(str(g["scene"]), w, h, float(g["aperture"]), float(g["focal_length"]), tex_scale=int(g["tex_scale"]))
+    ref = O.ref_trace(sc, S.make_seeds(int(g["seed"]), w * h), spp)
+    assert np.array_equal(ref, g["rgba"])

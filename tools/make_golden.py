@@ -1,8 +1,9 @@
 """Generates tests/golden/*.npz: small renders by the CPU oracle (fp64) on fixed seeds.
 
-The reference cannot be executed in this image (no Go, no OpenCL), so these fixtures pin the
-ORACLE (regression guard) rather than the reference; the GPU parity tests compare the CUDA path
-with both the live oracle and these files.  Re-run only when the oracle's semantics change:
+The oracle is held bit-identical to the reference's own kernel (tracer.cl compiled for the CPU, oracle/_ref), and
+tests/test_oracle_vs_reference.py checks that the compiled reference kernel reproduces every one of these files bit for
+bit -- so they are outputs of the reference itself, usable where /root/reference does not exist (the GPU box).  The GPU
+parity tests compare the CUDA path with both the live oracle and these files.  Re-run only if the reference changes:
 
     python tools/make_golden.py
 """
