@@ -131,8 +131,24 @@ def ref_lib() -> Optional[C.CDLL]:
         L.ref_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]
+        L.ref_closest.restype = C.c_int
+        L.ref_closest.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _ref_lib = L
     return _ref_lib
+
+
+def ref_closest(scene, rays: np.ndarray) -> np.ndarray:
+    """The reference's own findClosestIntersection (tracer.cl:537-742) for world-space rays [n, 6] (origin, direction).
+    Returns [n, 8]: t, object index (-1 = none), recorded normal xyz, recorded colour rgb."""
+    L = ref_lib()
+    if L is None:
+        raise RuntimeError("the compiled reference kernel is not available")
+    rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+    out = np.zeros((rays.shape[0], 8), dtype=np.float64)
+    L.ref_closest(scene.objects.ctypes.data, scene.n_objects, scene.triangles.ctypes.data if scene.n_triangles else None,
+                  scene.n_triangles, scene.groups.ctypes.data if scene.n_groups else None, scene.n_groups, rays.ctypes.data,
+                  rays.shape[0], out.ctypes.data)
+    return out
 
 
 def ref_trace(scene, seeds: np.ndarray, samples: int, rows: Optional[Tuple[int, int]] = None,

@@ -75,6 +75,30 @@ int ref_trace(const void* objects, int n_objects, const void* triangles, int n_t
     return 0;
 }
 
-int ref_abi(void) { return 1; }
+// The reference's findClosestIntersection (tracer.cl:537-742) for `n_rays` world-space rays (6 doubles each: origin,
+// direction).  Per ray, out[8] = t, object index (-1: none), the recorded normal xyz and colour rgb of the winning record
+// (meaningful for triangles; tracer.cl:669-671).
+int ref_closest(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,
+                const double* rays, int n_rays, double* out) {
+    static const refcl::triangle zero_tri = {};
+    static const refcl::group zero_group = {};
+    refcl::triangle* tris = const_cast<refcl::triangle*>(n_triangles > 0 ? static_cast<const refcl::triangle*>(triangles) : &zero_tri);
+    refcl::group* grps = const_cast<refcl::group*>(n_groups > 0 ? static_cast<const refcl::group*>(groups) : &zero_group);
+    std::vector<refcl::object> local(static_cast<const refcl::object*>(objects), static_cast<const refcl::object*>(objects) + n_objects);
+    for (int r = 0; r < n_rays; ++r) {
+        const double* q = rays + 6 * r;
+        refcl::context ctx = {};
+        const refcl::intersection ix = refcl::findClosestIntersection(local.data(), unsigned(n_objects), grps, tris, double4(q[0], q[1], q[2], 1.0),
+                                                                      double4(q[3], q[4], q[5], 0.0), &ctx);
+        double* o = out + 8 * r;
+        o[0] = ix.t; o[1] = double(ix.lowestIntersectionIndex);
+        const int k = ix.normalIndex >= 0 ? ix.normalIndex : 0;
+        o[2] = ctx.xsTriangle[k].x; o[3] = ctx.xsTriangle[k].y; o[4] = ctx.xsTriangle[k].z;
+        o[5] = ctx.xsTriangleColor[k].x; o[6] = ctx.xsTriangleColor[k].y; o[7] = ctx.xsTriangleColor[k].z;
+    }
+    return 0;
+}
+
+int ref_abi(void) { return 2; }
 
 }  // extern "C"

@@ -393,3 +393,35 @@ def test_two_mesh_objects_get_separate_roots_over_shared_triangles():
     # ranks restart per object; reference nodes of the second object point into its own node range
     assert sorted(m["tri_info"][:n, 0].tolist()) == sorted(m["tri_info"][n:, 0].tolist()) == list(range(n))
     assert m["tri_info"][:n, 1].max() < r1[1] <= m["tri_info"][n:, 1].min()
+
+
+# ---- the same question put to the reference's own code ---------------------------------------------------------------
+from oracle import oracle as _O  # noqa: E402  (test infrastructure)
+
+
+@pytest.mark.skipif(_O.ref_lib() is None, reason="no compiled reference kernel (oracle/_ref)")
+@pytest.mark.parametrize("name,n_rays", [("teapot", 900), ("gopher", 600)])
+def test_replayed_walk_picks_the_winner_of_the_reference_kernels_own_walk(name, n_rays):
+    """findClosestIntersection of the reference's tracer.cl (compiled for the CPU, oracle/_ref) on a scene that holds
+    only the mesh object, untransformed: the replayed device walk must return exactly its t -- also for rays with zero /
+    sub-EPSILON direction components, rays from inside the mesh and rays aimed at vertices."""
+    sc = S.build_scene(name, 32, 24)
+    m, obj = index_of(sc)
+    rec = sc.objects_view()[obj:obj + 1].copy()
+    eye = np.eye(4).ravel()
+    rec["transform"][0], rec["inverse"][0], rec["inverse_transpose"][0] = eye, eye, eye
+    only = S.SceneBuffers(name + "-only", 32, 24, rec.view(np.uint8).reshape(-1), sc.triangles, sc.groups, sc.camera)
+    obj_lo, obj_hi = np.array(rec["bb_min"][0][:3]), np.array(rec["bb_max"][0][:3])
+    rng = np.random.default_rng(21)
+    rays = rays_for(m, obj_lo, obj_hi, rng, n_rays)
+    ref = _O.ref_closest(only, np.array([np.concatenate([o, d]) for o, d in rays]))
+    stats = {"nodes": 0, "leaves": 0}
+    hits = 0
+    for i, (o, d) in enumerate(rays):
+        slot, t = replayed_winner(m, m["mesh"][obj], obj_lo, obj_hi, o, d, 1024.0, stats)
+        if ref[i, 1] < 0:
+            assert slot < 0, f"ray {i}: the reference hits nothing, the replay hits slot {slot}"
+        else:
+            hits += 1
+            assert slot >= 0 and t == ref[i, 0], f"ray {i}: replay (slot {slot}, t {t!r}) vs reference t {ref[i, 0]!r}"
+    assert hits > n_rays // 4
