@@ -1,17 +1,21 @@
 // Package cuda is the cgo binding that replaces internal/ocl's OpenCL driver in
 // eriklupander/pathtracer-ocl with libptcuda (hand-written sm_100a kernels behind a C ABI).
 //
-// It is a drop-in for the two things the rest of the Go program uses from internal/ocl:
+// It is a drop-in for the two things the rest of the Go program uses from the OpenCL side:
 //
 //	ocl.Trace(objects, triangles, groups, deviceIndex, samples, camera, textures, sphereTextures, cubeTextures) []float64
 //	    (internal/ocl/ocltracer.go:100)  ->  cuda.Trace(... same arguments ...)
 //	listDevices()  (cmd/pt/main.go:98-112)  ->  cuda.ListDevices()
 //
-// The scene records (ocl.CLObject / CLTriangle / CLGroup / CLCamera) are passed through untouched:
-// libptcuda consumes the same packed bytes the OpenCL kernel did (include/ptwire.h).
+// The scene records (CLObject / CLTriangle / CLGroup / CLCamera, ocltracer.go:25-96) are passed through
+// untouched: libptcuda consumes the same packed bytes the OpenCL kernel did (include/ptwire.h).  This package
+// does NOT import internal/ocl -- that package's ocltracer.go pulls in github.com/jgillich/go-opencl/cl (cgo,
+// OpenCL headers).  Trace is generic over the record types instead and checks their sizes (1024 / 512 / 256 /
+// 256 bytes) at the call, so the call site in renderer.go compiles unchanged with the structs wherever they
+// live, and internal/cuda itself builds with no OpenCL header, ICD or runtime present.
 //
-// NOTE: this file was written without a Go toolchain (none exists in the build image); it has been
-// checked by eye against include/ptcuda.h only.  See INTEGRATION.md for the build line.
+// NOTE: no Go toolchain exists in the image this was written in.  The C side of every call below is exercised,
+// with exactly these argument shapes, by tests/c_abi_smoke.c; the Go side has been checked by eye only.
 package cuda
 
 /*
@@ -29,16 +33,26 @@ import (
 	"math/rand"
 	"unsafe"
 
-	"github.com/eriklupander/pathtracer-ocl/internal/ocl"
 	"github.com/sirupsen/logrus"
 )
 
-// Options selects what the OpenCL path could not: arithmetic precision, RNG evaluation, several GPUs.
+// Wire record sizes (include/ptwire.h; ocltracer.go:25-96).
+const (
+	objectBytes   = 1024
+	triangleBytes = 512
+	groupBytes    = 256
+	cameraBytes   = 256
+)
+
+// Options selects what the OpenCL path could not: arithmetic precision, RNG evaluation, several GPUs,
+// and the two code paths upstream ships disabled.
 type Options struct {
-	FP64    bool    // false: fp32 mode (default), true: fp64, the arithmetic of tracer.cl
-	FastRNG bool    // cheaper evaluation of the same noise3D hash (still reproducible)
-	Devices []int32 // GPUs driven by this process; nil = {deviceIndex}
-	Seeds   []float64
+	FP64         bool    // false: fp32 mode (default), true: fp64, the precision of tracer.cl
+	FastRNG      bool    // cheaper evaluation of the same noise3D hash (still reproducible)
+	Devices      []int32 // GPUs driven by this process; nil = {deviceIndex}
+	Seeds        []float64
+	NEE          bool // next-event estimation (tracer.cl:786-825, call commented out at :1168)
+	CylinderCaps bool // cylinder end caps (tracer.cl:282-310, disabled at :437-444)
 }
 
 // ListDevices prints what the reference's --list-devices prints (cmd/pt/main.go:98-112).
@@ -52,9 +66,10 @@ func ListDevices() {
 	}
 }
 
-// Trace has the signature of ocl.Trace (internal/ocl/ocltracer.go:100).
-func Trace(objects []ocl.CLObject, triangles []ocl.CLTriangle, groups []ocl.CLGroup, deviceIndex, samples int,
-	camera ocl.CLCamera, textures []image.Image, sphereTextures []image.Image, cubeTextures []image.Image) []float64 {
+// Trace has the shape of ocl.Trace (internal/ocl/ocltracer.go:100): called with []CLObject, []CLTriangle,
+// []CLGroup and a CLCamera it needs no type arguments at the call site.
+func Trace[O, T, G, Cam any](objects []O, triangles []T, groups []G, deviceIndex, samples int,
+	camera Cam, textures []image.Image, sphereTextures []image.Image, cubeTextures []image.Image) []float64 {
 	return TraceWithOptions(objects, triangles, groups, deviceIndex, samples, camera, textures, sphereTextures, cubeTextures, Options{})
 }
 
@@ -82,11 +97,28 @@ func packTextures(imgs []image.Image) ([]byte, int, int, int) {
 	return all, w, h, len(imgs)
 }
 
-func TraceWithOptions(objects []ocl.CLObject, triangles []ocl.CLTriangle, groups []ocl.CLGroup, deviceIndex, samples int,
-	camera ocl.CLCamera, textures []image.Image, sphereTextures []image.Image, cubeTextures []image.Image, opt Options) []float64 {
+func checkSize[R any](what string, want uintptr) {
+	var zero R
+	if unsafe.Sizeof(zero) != want {
+		logrus.Fatalf("cuda.Trace: %s records are %d bytes, the wire format has %d", what, unsafe.Sizeof(zero), want)
+	}
+}
 
-	numPixels := int(camera.Width * camera.Height)
-	logrus.Infof("trace with %d objects %dx%d", len(objects), camera.Width, camera.Height)
+func TraceWithOptions[O, T, G, Cam any](objects []O, triangles []T, groups []G, deviceIndex, samples int,
+	camera Cam, textures []image.Image, sphereTextures []image.Image, cubeTextures []image.Image, opt Options) []float64 {
+
+	checkSize[O]("object", objectBytes)
+	checkSize[T]("triangle", triangleBytes)
+	checkSize[G]("group", groupBytes)
+	checkSize[Cam]("camera", cameraBytes)
+	if len(objects) == 0 {
+		logrus.Fatalf("cuda.Trace: scene has no objects")
+	}
+	// CLCamera starts with Width, Height int32 (ocltracer.go:86-87)
+	dims := (*[2]int32)(unsafe.Pointer(&camera))
+	width, height := int(dims[0]), int(dims[1])
+	numPixels := width * height
+	logrus.Infof("trace with %d objects %dx%d", len(objects), width, height)
 
 	// one random double per pixel, as computeBatch does per batch (ocltracer.go:260-263)
 	seeds := opt.Seeds
@@ -125,6 +157,13 @@ func TraceWithOptions(objects []ocl.CLObject, triangles []ocl.CLTriangle, groups
 	if opt.FastRNG {
 		rngMode = C.PTC_RNG_FAST
 	}
+	features := C.int32_t(0)
+	if opt.NEE {
+		features |= C.PTC_FEATURE_NEE
+	}
+	if opt.CylinderCaps {
+		features |= C.PTC_FEATURE_CYLINDER_CAPS
+	}
 	devices := opt.Devices
 	if devices == nil {
 		devices = []int32{int32(deviceIndex)}
@@ -132,9 +171,9 @@ func TraceWithOptions(objects []ocl.CLObject, triangles []ocl.CLTriangle, groups
 
 	results := make([]float64, numPixels*4)
 	errbuf := make([]byte, 512)
-	rc := C.ptc_render_flat(unsafe.Pointer(&objects[0]), C.int32_t(len(objects)), triPtr, C.int32_t(len(triangles)),
+	rc := C.ptc_render_flat2(unsafe.Pointer(&objects[0]), C.int32_t(len(objects)), triPtr, C.int32_t(len(triangles)),
 		grpPtr, C.int32_t(len(groups)), unsafe.Pointer(&camera), tex[0], tex[1], tex[2], &texDims[0],
-		(*C.double)(unsafe.Pointer(&seeds[0])), C.int32_t(samples), precision, rngMode,
+		(*C.double)(unsafe.Pointer(&seeds[0])), C.int32_t(samples), precision, rngMode, features,
 		(*C.int32_t)(unsafe.Pointer(&devices[0])), C.int32_t(len(devices)),
 		(*C.double)(unsafe.Pointer(&results[0])), (*C.char)(unsafe.Pointer(&errbuf[0])), C.int(len(errbuf)))
 	if rc != 0 {

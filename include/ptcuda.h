@@ -27,7 +27,12 @@
  *   - errors: the reference aborts via logrus.Fatalf; these functions return non-zero and write
  *     a message into `err` instead, the Go wrapper turns that back into Fatalf;
  *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails.
- *   - thread-compatible: no global mutable state; distinct contexts may be used concurrently.
+ *   - thread-compatible: distinct contexts may be used concurrently.  The only process-wide state is a
+ *     mutex-protected table of per-device memory pools (driver handles) that keeps a bounded amount of device
+ *     memory between calls; ptc_trim() returns it.
+ *   - arithmetic: PTC_FP64 evaluates tracer.cl's formulas in double but not operation by operation (fused multiply-add,
+ *     reciprocal multiplies, spheres intersected in world space), so it agrees with the reference to the 1e-6 gate, not
+ *     bit for bit; decisions that sit exactly on a threshold can differ.  Only the CPU oracle is bit-exact.
  */
 #ifndef PTCUDA_H
 #define PTCUDA_H
@@ -42,10 +47,19 @@ extern "C" {
 
 /* precision */
 #define PTC_FP32 0   /* fp32 arithmetic mode (north_star: "fp32 mode", tolerance 1e-3 at 1 spp)   */
-#define PTC_FP64 1   /* fp64 arithmetic mode, matches tracer.cl            (tolerance 1e-6 at 1 spp) */
+#define PTC_FP64 1   /* fp64 arithmetic mode, tracer.cl's own precision   (tolerance 1e-6 at 1 spp) */
+
+/* ptc_job.features: code paths the reference ships switched off (they change the image; default 0 = as upstream) */
+#define PTC_FEATURE_NEE           1  /* next-event estimation, tracer.cl:786-825 (call commented out at :1168)    */
+#define PTC_FEATURE_CYLINDER_CAPS 2  /* cylinder end caps, tracer.cl:282-310 (disabled at :437-444)              */
+
+/* frame formats (ptc_frame_*) */
+#define PTC_FRAME_F64 0  /* 4 doubles per pixel, what ptc_read returns */
+#define PTC_FRAME_F32 1  /* 4 floats per pixel: half the NVLink / PCIe bytes */
+#define PTC_FRAME_HANDLE_BYTES 64
 
 /* rng_mode */
-#define PTC_RNG_PARITY 0 /* canonical noise3D stream, bit-identical to the oracle (oracle/README.md) */
+#define PTC_RNG_PARITY 0 /* canonical noise3D stream, bit-identical to the oracle (oracle/canon_rng.h)  */
 #define PTC_RNG_FAST   1 /* same hash, hardware-approximated sin; statistically validated only       */
 
 typedef struct ptc_job {
@@ -84,7 +98,8 @@ typedef struct ptc_job {
     int32_t shard_count;
     int32_t rows_per_tile;        /* 0 => 4, the reference's batch height (ocltracer.go:214) */
 
-    int32_t reserved[8];          /* must be zero */
+    int32_t features;             /* PTC_FEATURE_* bits; 0 = the reference's behaviour */
+    int32_t reserved[7];          /* must be zero */
 } ptc_job;
 
 typedef struct ptc_stats {
@@ -102,6 +117,7 @@ typedef struct ptc_stats {
 } ptc_stats;
 
 typedef struct ptc_context ptc_context;
+typedef struct ptc_frame ptc_frame;
 
 /* --list-devices support.  ptc_device_count returns the number of CUDA devices (0 if none or if
  * the driver is unusable).  ptc_device_name returns 0 and a NUL-terminated name, non-zero on a
@@ -122,6 +138,14 @@ int ptc_render_flat(const void *objects, int32_t n_objects, const void *triangle
                     int32_t rng_mode, const int32_t *devices, int32_t n_devices, double *out_rgba,
                     char *err, int errlen);
 
+/* ptc_render_flat with the ptc_job.features bits as one more argument. */
+int ptc_render_flat2(const void *objects, int32_t n_objects, const void *triangles, int32_t n_triangles,
+                     const void *groups, int32_t n_groups, const void *camera,
+                     const uint8_t *tex_plane, const uint8_t *tex_sphere, const uint8_t *tex_cube,
+                     const int32_t *tex_dims, const double *seeds, int32_t samples, int32_t precision,
+                     int32_t rng_mode, int32_t features, const int32_t *devices, int32_t n_devices,
+                     double *out_rgba, char *err, int errlen);
+
 /* Phase API. */
 int  ptc_open(const ptc_job *job, ptc_context **ctx, char *err, int errlen);
 int  ptc_trace(ptc_context *ctx, char *err, int errlen);   /* launches + waits; result stays in HBM */
@@ -141,14 +165,42 @@ int ptc_reset(ptc_context *ctx, char *err, int errlen);
  * no gamma, clamp(round(c*255)), alpha 255): rows*width*4 bytes, 8x less readback than ptc_read. */
 int ptc_read_rgba8(ptc_context *ctx, uint8_t *out_rgba8, char *err, int errlen);
 
+/* The frame as 4 floats per pixel (SURVEY.md 8f-2 "RGBA8 + optional f32"; the reference's .raw writer and canvas
+ * hold single-precision-range data, internal/app/raw/writer.go:11-35): rows*width*4 floats, half of ptc_read's bytes. */
+int ptc_read_f32(ptc_context *ctx, float *out_rgba_f32, char *err, int errlen);
+
 /* Replace the per-pixel seeds of an open context (width*height doubles, same layout as
  * ptc_job.seeds).  Mirrors the reference drawing fresh seeds for every batch. */
 int ptc_set_seeds(ptc_context *ctx, const double *seeds, char *err, int errlen);
 
 /* Device-resident result of local device `local_index` (0..n_devices-1): pointer to its packed
- * rows (rows * width * 4 doubles), for callers that gather on the device themselves (NCCL). */
+ * rows (rows * width * 4 doubles), for callers that gather on the device themselves (NCCL).  A context that
+ * drives several peer-connected devices gathers inside its kernels: local device 0 then exposes ALL the
+ * context's rows and the other devices report 0 doubles. */
 int ptc_device_framebuffer(ptc_context *ctx, int local_index, void **dev_ptr, int64_t *n_doubles,
                            int32_t *cuda_device);
+
+/* Frames: the final gather fused into the trace kernel.  A frame is a whole-image buffer
+ * (width*height RGBA pixels, row-major, top row first) on ONE device.  A context with a frame attached stores each
+ * finished pixel straight into it, addressed by frame row -- from the owning device locally, from any other device
+ * as NVLink peer stores out of the kernel's epilogue -- so N sharded contexts (N GPUs of one process, or N processes
+ * through ptc_frame_export / ptc_frame_import, CUDA IPC) leave the complete image on the frame's device with no copy
+ * kernel, no staging buffer and no collective; the caller only has to order "all shards traced" before
+ * ptc_frame_read (a barrier between processes).  Replaces the per-batch EnqueueReadBuffer of ocltracer.go:355-373.
+ *   ptc_frame_create    allocate on `device` (zero-filled)
+ *   ptc_frame_export    64-byte handle another process passes to ptc_frame_import (only the creator may export)
+ *   ptc_frame_import    map another process's frame for stores from `device`
+ *   ptc_set_frame       attach (or, with NULL, detach) -- ptc_read* then refuse, the pixels are in the frame
+ *   ptc_frame_read      device -> host copy of the whole frame (width*height*4 doubles or floats)
+ *   ptc_frame_device_pointer  the raw buffer, for callers that keep the image on the device */
+int  ptc_frame_create(int device, int32_t width, int32_t height, int32_t format, ptc_frame **frame, char *err, int errlen);
+int  ptc_frame_export(ptc_frame *frame, void *handle64, char *err, int errlen);
+int  ptc_frame_import(int device, const void *handle64, int32_t width, int32_t height, int32_t format,
+                      ptc_frame **frame, char *err, int errlen);
+int  ptc_set_frame(ptc_context *ctx, ptc_frame *frame, char *err, int errlen);
+int  ptc_frame_read(ptc_frame *frame, void *out, char *err, int errlen);
+int  ptc_frame_device_pointer(ptc_frame *frame, void **dev_ptr, int64_t *bytes, int32_t *cuda_device);
+void ptc_frame_destroy(ptc_frame *frame);
 
 /* Rows owned by this context, in increasing order; returns the count, fills at most `cap`. */
 int ptc_shard_rows(const ptc_context *ctx, int32_t *rows, int cap);
@@ -160,7 +212,8 @@ int ptc_plan_rows(int32_t height, int32_t rows_per_tile, int32_t shard_index, in
                   int32_t *rows, int cap);
 
 /* Single-GPU contexts draw device memory from a per-device pool that is kept between calls so a
- * render pays no cudaMalloc/cudaFree; ptc_trim returns the pooled memory to the driver. */
+ * render pays no cudaMalloc/cudaFree.  The pool retains at most 768 MB per device after a context closes;
+ * ptc_trim returns that too. */
 void ptc_trim(void);
 
 const char *ptc_version(void);

@@ -32,10 +32,15 @@
 //     The fp32 instantiation uses the SFU approximations (rcp / rsqrt / sqrt / sin / cos) for its
 //     own arithmetic; the RNG and the texture filter stay exactly rounded in both modes.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "rng.cuh"
+
+#ifndef PTK_KERNEL_VERSION
+#define PTK_KERNEL_VERSION "r02v1"      // names the ncu captures under profiles/ that belong to this kernel source
+#endif
 
 namespace ptk {
 
@@ -55,18 +60,17 @@ namespace ptk {
 #ifndef PTK_MESH_MIN_BLOCKS
 #define PTK_MESH_MIN_BLOCKS 8
 #endif
-#ifndef PTK_UNROLL_SLOTS
-// Compile-time object slots (constant-bank immediates instead of indexed constant loads) for mesh-free
-// scenes.  Measured on B200: SLOWER than the run loop (9.36 vs 10.64 Gpaths/s on the reference scene --
-// 16 copies of every object test cost more in instruction fetch than the loads they save), so it is off.
-#define PTK_UNROLL_SLOTS 0
-#endif
 #ifndef PTK_BLOCK_THREADS
 #define PTK_BLOCK_THREADS 128
 #endif
 
 constexpr int kMaxObjects = 16;
+// Unrolled slots of the intersection loop (see Params::fast): three runs in scene order -- spheres, planes, spheres --
+// which is how Cornell-box scenes are laid out (light first, walls, then the contents).
+constexpr int kFastA = 4, kFastB = 8, kFastC = 6, kFastSlots = kFastA + kFastB + kFastC;
 constexpr int kBlockThreads = PTK_BLOCK_THREADS;
+constexpr int kBlockWarps = kBlockThreads / 32;
+constexpr int kMaxCluster = 8;             // CTAs per cluster (portable limit): up to kMaxCluster * kBlockWarps sample slices per pixel
 constexpr int kTileW = 8, kTileH = 4;   // pixels covered by one warp
 
 template <typename R> struct alignas(16) V4 { R x, y, z, w; };
@@ -146,9 +150,19 @@ template <typename R> struct alignas(16) DObjShade {
     R pad1[3];
 };
 
-// Consecutive objects of one type form a run; the intersection loop dispatches once per run and
-// keeps the reference's object order (ties go to the lower object index, tracer.cl:731-739).
-struct DRun { int type, begin, end, pad; };
+// "Fast" objects: planes and spheres whose `inverse` is a similarity -- what Cornell-box scenes are made of.  They are
+// tested by code that is unrolled per SLOT: slot K's record sits at a fixed offset of the kernel parameter block, so
+// its coefficients reach the FFMAs through one uniform 128-bit constant load -- no per-lane load, no index arithmetic,
+// no type dispatch (round 1's run loop spent ~17 % of all issue slots on exactly that).  A record is
+//   plane:  (a, b, c, d) = row 1 of `inverse`: object-space y of a point is a*x + b*y + c*z + d (tracer.cl:478-483)
+//   sphere: (cx, cy, cz, r^2): the world-space sphere |p - c|^2 = r^2 that the unit sphere maps to when `inverse` is a
+//           similarity (scale s = 1/r): t solves |ro + t*rd - c|^2 = r^2, the reference's quadratic (tracer.cl:448-476)
+//           divided through by s^2.
+// Slots form three runs -- kFastA spheres, kFastB planes, kFastC spheres -- filled by the host with the longest
+// subsequence of the scene's objects that fits "spheres, planes, spheres" in scene order; each run stops at its count.
+// Fast objects therefore meet in scene order and ties resolve as upstream (first recorded wins, tracer.cl:731-739);
+// everything else goes through the slow loop, which compares (t, object index) explicitly.
+template <typename R> struct alignas(16) DFast { R a, b, c, d; };
 
 template <typename R> struct DCam {
     R pixel_size, half_width, half_height, aperture, focal_length;
@@ -171,8 +185,12 @@ constexpr int kWideStack = 96;                 // deferred-child stack entries p
 constexpr int kEmptyChild = (int)0x80000000;
 
 template <typename R> struct Params {
-    DObjHot<R> hot[kMaxObjects];
-    DRun runs[kMaxObjects];     int n_runs;
+    DFast<R> fast[kFastSlots];  // runs A (spheres) | B (planes) | C (spheres)
+    int fast_n[4];              // objects in run A, B, C
+    int fast_obj[kFastSlots];   // slot -> object index
+    DObjHot<R> hot[kMaxObjects];    // read by the slow loop and the mesh walk only
+    int slow_obj[kMaxObjects];  int n_slow;    // analytic objects outside the fast slots (general spheres, cylinders, cubes, overflow), scene order
+    int mesh_obj[kMaxObjects];  int n_mesh;    // group objects with triangles, scene order
     const DObjShade<R>* shade;  int n_objects;
     // reference BVH (the caller's groups) re-emitted in the reference's visiting order: only the boxes and the
     // parent links are kept, for the "would the reference have tested this triangle" check
@@ -190,14 +208,22 @@ template <typename R> struct Params {
     const R* lens;              // 2 per sample: sunflower(samples, 2, n), tracer.cl:235-248 (NULL without DoF)
     DCam<R> cam;
     DTex tex[3];
-    const double* seeds;        // full frame, row-major
+    const double* seeds;        // one per OWNED pixel: local rows, row-major
     const int* row_map;         // local row -> frame row
-    double* out;                // rows * width * 4 (RGBA), or per-slice partial sums when slices > 1
+    void* out;                  // RGBA result, double4 (float4 when out_f32) per pixel, row-major, `width` pixels per row
+    const int* out_row;         // local row -> row of `out`; NULL: rows are packed in local order.  With a map `out` may be a
+                                // buffer shared by several devices (a peer device's memory, or another process's through
+                                // CUDA IPC): the gather is then fused into this kernel's epilogue as NVLink stores
+    double4* acc;               // progressive rendering: running per-pixel sums (local rows), or NULL
+    int out_f32;
+    int nee, caps;              // optional features the reference ships disabled (tracer.cl:1168, :437-444); 0 = upstream behaviour
     int rows;                   // local rows rendered by this device
     int samples;                // total samples per pixel (enters the RNG seeding and the final weight)
     int sample_begin, sample_end;   // samples rendered by this launch: [begin, end) (0, samples for a full render)
-    int raw_sums;               // 1: write unweighted sums per slice even when slices == 1 (progressive accumulation)
-    int slices;                 // sample slices per pixel (gridDim.y)
+    int slices;                 // sample slices per pixel: a power of two <= kBlockWarps * cluster size
+    int slices_per_block;       // min(slices, kBlockWarps): the warps of a block are slices_per_block slices of
+                                // kBlockWarps / slices_per_block tiles; a cluster holds all slices of its tiles
+    int stack_entries;          // mesh walk: entries of one 8-lane group's stack in dynamic shared memory (scene's worst case + 1)
     R pi;                       // (double)3.14159265359f, tracer.cl:1
     R eps;                      // 0.0001, tracer.cl:4
 };
@@ -350,27 +376,6 @@ template <typename R> struct Hit {
     int tri;    // winning triangle (groups)
     R u, v;     // its barycentrics (normal interpolation, tracer.cl:669)
 };
-
-// A candidate wins iff EPS < t < current best: strict '<' keeps the first-recorded hit on ties,
-// the reference's selection rule (tracer.cl:731-739).  NaN fails both comparisons.
-template <typename R> __device__ __forceinline__ void offer(Hit<R>& h, R t, int obj, R eps) {
-    if (t > eps && t < h.t) { h.t = t; h.obj = obj; }
-}
-
-// Roots of the sphere quadratic, tracer.cl:465-475: recorded only when the discriminant is strictly
-// positive.  Branch-free: a non-positive discriminant turns the roots into NaN, which offer() rejects.
-// The quadratic is evaluated in its half-b form: with hb = dot(d,o) the reference's b = 2*hb,
-// b*b - 4*a*c = 4*(hb*hb - a*c) and 2*a differ from these only by exact powers of two, so
-// (-hb -+ sqrt(hb*hb - a*c)) / a is the same floating-point value as upstream's (-b -+ sqrt(disc)) / (2a).
-template <typename R> __device__ __forceinline__ void sphere_roots(Hit<R>& h, V3<R> o, V3<R> d, int j, R eps) {
-    const R a = dot(d, d), hb = dot(d, o), c = dot(o, o) - R(1);
-    const R disc4 = hb * hb - a * c;
-    R sq = m_sqrt(disc4);
-    sq = disc4 > R(0) ? sq : m_huge<R>() * R(0);
-    const R inv_a = m_rcp(a);
-    offer(h, (-hb - sq) * inv_a, j, eps);
-    offer(h, (-hb + sq) * inv_a, j, eps);
-}
 
 // ---- mesh objects: rebuilt BVH, reference semantics ------------------------------------------------
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -583,12 +588,11 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& o
 // All mesh objects of the scene (tracer.cl:598-720), after the analytic objects.  Called by all 32 lanes.
 template <typename R>
 __device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h, int2* __restrict__ stk) {
-    for (int r = 0; r < P.n_runs; ++r) {
-        if (P.runs[r].type != 4) continue;
-        for (int j = P.runs[r].begin; j < P.runs[r].end; ++j) {
+    {
+        for (int q = 0; q < P.n_mesh; ++q) {
+            const int j = P.mesh_obj[q];
             const DObjHot<R>& ob = P.hot[j];
             const DMesh<R>& m = P.mesh[j];
-            if (m.bvh_root < 0) continue;
             const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
             const Slab<R> s = make_slab(d, P.eps);
             R t0, t1, tn;
@@ -602,21 +606,74 @@ __device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R>
     }
 }
 
-// One analytic object against one ray (`type` is warp-uniform).
+// A candidate of the slow loop: objects there are NOT visited in scene order relative to the fast slots, so the
+// reference's "first recorded wins" (tracer.cl:731-739) is spelled out: on equal t the lower object index wins.
+template <typename R> __device__ __forceinline__ void offer_ordered(Hit<R>& h, R t, int obj, R eps) {
+    if (t > eps && (t < h.t || (t == h.t && obj < h.obj))) { h.t = t; h.obj = obj; }
+}
+
+// Fast slots, unrolled (see DFast).  `a` = dot(rd, rd) and `inv_a` = 1 / a are per-ray values shared by every sphere
+// slot.  The winner is tracked as a SLOT number (an immediate); closest_analytic maps it to the object index once.
+template <typename R> __device__ __forceinline__ R fma3(R a, R x, R b, R y, R c, R z, R d) { return a * x + (b * y + (c * z + d)); }
+// sqrt(disc) for disc > 0, NaN otherwise (the reference records roots only when disc > 0, tracer.cl:465): in float
+// disc * rsqrt(disc) does it without a compare -- rsqrt(0) = inf, inf * 0 = NaN, rsqrt(negative) = NaN
+__device__ __forceinline__ float sqrt_pos(float disc) { return disc * m_rsqrt(disc); }
+__device__ __forceinline__ double sqrt_pos(double disc) { return disc > 0.0 ? sqrt(disc) : __longlong_as_double(0x7ff8000000000000LL); }
+
+template <typename R, int SLOT>
+__device__ __forceinline__ void fast_plane(const Params<R>& P, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
+    const DFast<R>& f = P.fast[SLOT];                            // tracer.cl:478-483: t = -o'.y / d'.y when |d'.y| > EPSILON
+    const R oy = fma3(f.a, ro.x, f.b, ro.y, f.c, ro.z, f.d);
+    const R dy = fma3(f.a, rd.x, f.b, rd.y, f.c, rd.z, R(0));
+    const R t = -oy * m_rcp(dy);
+    if (m_abs(dy) > eps && t > eps && t < h.t) { h.t = t; h.obj = SLOT; }
+}
+template <typename R, int SLOT>
+__device__ __forceinline__ void fast_sphere(const Params<R>& P, V3<R> ro, V3<R> rd, R a, R inv_a, R eps, Hit<R>& h) {
+    const DFast<R>& f = P.fast[SLOT];                            // tracer.cl:448-476: both roots recorded when disc > 0
+    const V3<R> oc = {ro.x - f.a, ro.y - f.b, ro.z - f.c};
+    const R hb = dot(rd, oc), c = dot(oc, oc) - f.d;
+    const R sq = sqrt_pos(hb * hb - a * c);
+    const R t0 = (-hb - sq) * inv_a, t1 = (-hb + sq) * inv_a;    // t0 <= t1: the first root beyond EPSILON is the pair's winner
+    const R t = t0 > eps ? t0 : t1;
+    if (t1 > eps && t < h.t) { h.t = t; h.obj = SLOT; }          // (NaN roots fail every comparison)
+}
+template <typename R, int K, int END>
+__device__ __forceinline__ void run_planes(const Params<R>& P, int n, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
+    if constexpr (K < END) {
+        if (K - kFastA >= n) return;
+        fast_plane<R, K>(P, ro, rd, eps, h);
+        run_planes<R, K + 1, END>(P, n, ro, rd, eps, h);
+    }
+}
+template <typename R, int K, int BEGIN, int END>
+__device__ __forceinline__ void run_spheres(const Params<R>& P, int n, V3<R> ro, V3<R> rd, R a, R inv_a, R eps, Hit<R>& h) {
+    if constexpr (K < END) {
+        if (K - BEGIN >= n) return;
+        fast_sphere<R, K>(P, ro, rd, a, inv_a, eps, h);
+        run_spheres<R, K + 1, BEGIN, END>(P, n, ro, rd, a, inv_a, eps, h);
+    }
+}
+
+// One analytic object of the slow loop against one ray (`type` is warp-uniform).
 template <typename R>
 __device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int type, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
     if (type == 0) {                                             // plane, tracer.cl:478-483
         R oy = ob.inv[4] * ro.x + ob.inv[5] * ro.y + ob.inv[6] * ro.z + ob.inv[7];
         R dy = ob.inv[4] * rd.x + ob.inv[5] * rd.y + ob.inv[6] * rd.z;
         R t = m_div(-oy, dy);
-        if (m_abs(dy) > eps) offer(h, t, j, eps);
-    } else if (type == 5) {                                      // sphere whose inverse is scale+translate only
-        V3<R> o = {ob.inv[0] * ro.x + ob.inv[3], ob.inv[5] * ro.y + ob.inv[7], ob.inv[10] * ro.z + ob.inv[11]};
-        V3<R> d = {ob.inv[0] * rd.x, ob.inv[5] * rd.y, ob.inv[10] * rd.z};    // (off-diagonal terms are exact zeros)
-        sphere_roots(h, o, d, j, eps);
+        if (m_abs(dy) > eps) offer_ordered(h, t, j, eps);
     } else if (type == 1) {                                      // sphere, tracer.cl:448-476
+        // Roots recorded only when the discriminant is strictly positive.  Half-b form: with hb = dot(d,o) the
+        // reference's b = 2*hb, b*b - 4*a*c = 4*(hb*hb - a*c) and 2*a differ from these by exact powers of two only.
         V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-        sphere_roots(h, o, d, j, eps);
+        const R a = dot(d, d), hb = dot(d, o), c = dot(o, o) - R(1);
+        const R disc4 = hb * hb - a * c;
+        if (disc4 > R(0)) {
+            const R sq = m_sqrt(disc4), inv_a = m_rcp(a);
+            offer_ordered(h, (-hb - sq) * inv_a, j, eps);
+            offer_ordered(h, (-hb + sq) * inv_a, j, eps);
+        }
     } else if (type == 2) {                                      // cylinder side, caps off, tracer.cl:396-446
         V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
         R a = d.x * d.x + d.z * d.z;
@@ -628,8 +685,8 @@ __device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int typ
                 R sq = m_sqrt(disc), inv_den = m_rcp(R(2) * a);
                 R t0 = (-b - sq) * inv_den, t1 = (-b + sq) * inv_den;
                 R y0 = o.y + t0 * d.y, y1 = o.y + t1 * d.y;
-                if (y0 > ob.aux[0] && y0 < ob.aux[1]) offer(h, t0, j, eps);
-                if (y1 > ob.aux[0] && y1 < ob.aux[1]) offer(h, t1, j, eps);
+                if (y0 > ob.aux[0] && y0 < ob.aux[1]) offer_ordered(h, t0, j, eps);
+                if (y1 > ob.aux[0] && y1 < ob.aux[1]) offer_ordered(h, t1, j, eps);
             }
         }
     } else if (type == 3) {                                      // cube, tracer.cl:378-394
@@ -637,37 +694,25 @@ __device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int typ
         Slab<R> s = make_slab(d, eps);
         R tmin, tmax;
         ray_box(o, d, s, R(-1), R(-1), R(-1), R(1), R(1), R(1), tmin, tmax);
-        if (!(tmin > tmax)) { offer(h, tmin, j, eps); offer(h, tmax, j, eps); }
+        if (!(tmin > tmax)) { offer_ordered(h, tmin, j, eps); offer_ordered(h, tmax, j, eps); }
     }
 }
 
-// Object slots unrolled at compile time: slot K reads P.hot[K] at a FIXED offset of the kernel
-// parameter block, so every matrix entry is an immediate constant-bank operand of its FFMA -- no
-// load instruction, no address arithmetic, no loop counter (the slot's type test is a uniform branch).
-template <typename R, int K>
-__device__ __forceinline__ void scan_slots(const Params<R>& P, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
-    if constexpr (K < kMaxObjects) {
-        if (K < P.n_objects) {
-            test_object<R>(P.hot[K], K, P.hot[K].type, ro, rd, eps, h);
-            scan_slots<R, K + 1>(P, ro, rd, eps, h);
-        }
-    }
-}
-
-// Analytic objects against one ray: tracer.cl:537-597 of findClosestIntersection.  Object order is the
-// scene's (ties go to the lower index, tracer.cl:731-739).  Mesh objects are handled by mesh_walk.
+// Analytic objects against one ray: tracer.cl:537-597 of findClosestIntersection.  Planes and similarity-transformed
+// spheres go through the unrolled fast slots in scene order; what remains (cylinders, cubes, stretched spheres, more
+// than kFastSlots fast objects) through a loop over the constant-bank records.  Mesh objects: closest_mesh.
 template <typename R>
 __device__ __forceinline__ void closest_analytic(const Params<R>& P, V3<R> ro, V3<R> rd, Hit<R>& h) {
     const R eps = P.eps;
     h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
-    if (PTK_UNROLL_SLOTS) {
-        scan_slots<R, 0>(P, ro, rd, eps, h);
-        return;
-    }
-    for (int r = 0; r < P.n_runs; ++r) {                 // one dispatch per run of consecutive same-type objects
-        const int type = P.runs[r].type, jb = P.runs[r].begin, je = P.runs[r].end;
-        if (type == 4) continue;
-        for (int j = jb; j < je; ++j) test_object<R>(P.hot[j], j, type, ro, rd, eps, h);
+    const R a = dot(rd, rd), inv_a = m_rcp(a);
+    run_spheres<R, 0, 0, kFastA>(P, P.fast_n[0], ro, rd, a, inv_a, eps, h);
+    run_planes<R, kFastA, kFastA + kFastB>(P, P.fast_n[1], ro, rd, eps, h);
+    run_spheres<R, kFastA + kFastB, kFastA + kFastB, kFastSlots>(P, P.fast_n[2], ro, rd, a, inv_a, eps, h);
+    if (h.obj >= 0) h.obj = P.fast_obj[h.obj];                   // slot -> object index
+    for (int k = 0; k < P.n_slow; ++k) {
+        const int j = P.slow_obj[k];
+        test_object<R>(P.hot[j], j, P.hot[j].type, ro, rd, eps, h);
     }
 }
 
@@ -833,31 +878,24 @@ __device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, P
     return (ob.emission[0] > R(0)) || !(s.b < 10u && s.effective < 4u);        // tracer.cl:1107, 884
 }
 
-// Frame geometry of a thread: a warp covers an 8x4 pixel tile.
-struct PixelSlot { int lx, ly, gy; bool has_pixel; };
-template <typename R> __device__ __forceinline__ PixelSlot pixel_slot(const Params<R>& P) {
+// Frame geometry of a thread.  A warp covers an 8x4 pixel tile for one sample slice.  The warps of a block are
+// slices_per_block slices of kBlockWarps / slices_per_block consecutive tiles; the blocks of a cluster hold the
+// remaining slices of the same tiles (slice = cluster rank * slices_per_block + slice within the block).
+struct PixelSlot { int lx, ly, gy, slice; bool has_pixel; };
+template <typename R> __device__ __forceinline__ PixelSlot pixel_slot(const Params<R>& P, unsigned cluster_rank, unsigned cluster_size) {
     const int W = P.cam.width;
     const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int spb = P.slices_per_block;                       // 1, 2 or 4 (power of two <= kBlockWarps)
+    const int tiles_per_block = kBlockWarps / spb;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = (int)(blockIdx.x / cluster_size) * tiles_per_block + w / spb;
     PixelSlot s;
-    s.lx = (warp % tiles_x) * kTileW + (lane & (kTileW - 1));
-    s.ly = (warp / tiles_x) * kTileH + (lane / kTileW);
+    s.slice = (int)cluster_rank * spb + (w % spb);
+    s.lx = (tile % tiles_x) * kTileW + (lane & (kTileW - 1));
+    s.ly = (tile / tiles_x) * kTileH + (lane / kTileW);
     s.has_pixel = s.lx < W && s.ly < P.rows;
     s.gy = s.has_pixel ? P.row_map[s.ly] : 0;
     return s;
-}
-
-template <typename R> __device__ __forceinline__ void store_pixel(const Params<R>& P, const PixelSlot& px, int slice, double col_r, double col_g, double col_b) {
-    const size_t pix = (size_t)px.ly * P.cam.width + px.lx;
-    if (P.slices == 1 && !P.raw_sums) {
-        const double wgt = 1.0 / (double)P.samples;                                  // tracer.cl:837, 1184-1187
-        double4* o = reinterpret_cast<double4*>(P.out) + pix;
-        *o = make_double4(col_r * wgt, col_g * wgt, col_b * wgt, 1.0);
-    } else {
-        double4* o = reinterpret_cast<double4*>(P.out) + ((size_t)slice * P.rows * P.cam.width + pix);
-        *o = make_double4(col_r, col_g, col_b, 0.0);
-    }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
@@ -865,13 +903,16 @@ template <typename R> __device__ __forceinline__ void store_pixel(const Params<R
 // stacks) compiled in.
 template <typename R, int RNG, bool GROUPS>
 __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS_F64) : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
-    __shared__ int2 mesh_stacks[GROUPS ? kBlockThreads / kWide : 1][GROUPS ? kWideStack + 1 : 1];   // one per 8-lane group
-    const PixelSlot px = pixel_slot(P);
+    extern __shared__ int2 mesh_stacks[];       // GROUPS: one stack of P.stack_entries per 8-lane group (sized by the host from the scene's BVH)
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned cluster_size = cluster.num_blocks(), cluster_rank = cluster.block_rank();
+    const PixelSlot px = pixel_slot(P, cluster_rank, cluster_size);
     const int lane = threadIdx.x & 31;
     const int W = P.cam.width;
-    const int slice = blockIdx.y;
+    const int slice = px.slice;
     const unsigned samples = (unsigned)P.samples;
-    const double seed = px.has_pixel ? P.seeds[(size_t)px.gy * W + px.lx] : 0.0;
+    const double seed = px.has_pixel ? P.seeds[(size_t)px.ly * W + px.lx] : 0.0;
     const float fgi = (float)(seed / (double)P.n_objects);     // tracer.cl:840
     const float fgi2 = (float)(seed / (double)samples);        // tracer.cl:841
     const R fx = R(px.lx), fy = R(px.gy);
@@ -924,7 +965,7 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
 
         Hit<R> h;
         closest_analytic<R>(P, s.ro, s.rd, h);
-        if (GROUPS) closest_mesh<R>(P, s.ro, s.rd, live, lane, h, mesh_stacks[threadIdx.x / kWide]);
+        if (GROUPS) closest_mesh<R>(P, s.ro, s.rd, live, lane, h, mesh_stacks + (threadIdx.x / kWide) * P.stack_entries);
 
         bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
         if (live && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);
@@ -935,25 +976,41 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
             fresh = true;
         }
     }
-    if (px.has_pixel) store_pixel(P, px, slice, col_sum[0][threadIdx.x], col_sum[1][threadIdx.x], col_sum[2][threadIdx.x]);
+
+    // Epilogue: the slices of a pixel meet here -- the warps of this block through shared memory, the blocks of the
+    // cluster through distributed shared memory -- and are summed in slice order (deterministic: the same order for
+    // any grid shape), so no per-slice partial sums ever go to HBM.  The first slice's thread of the cluster's first
+    // block owns the pixel's store; with out_frame_rows that store goes straight into the (possibly remote) frame.
+    if (cluster_size > 1) cluster.sync(); else __syncthreads();
+    const int spb = P.slices_per_block;
+    const int w = threadIdx.x >> 5;
+    if (cluster_rank == 0 && (w % spb) == 0 && px.has_pixel) {
+        double r = 0.0, g = 0.0, b = 0.0;
+        const size_t lpix = (size_t)px.ly * W + px.lx;
+        if (P.acc) { const double4 a = P.acc[lpix]; r = a.x; g = a.y; b = a.z; }
+        for (unsigned cr = 0; cr < cluster_size; ++cr) {
+            const double* remote = cluster_size > 1 ? cluster.map_shared_rank(&col_sum[0][0], cr) : &col_sum[0][0];
+            for (int q = 0; q < spb; ++q) {
+                const int t = threadIdx.x + 32 * q;
+                r += remote[t]; g += remote[kBlockThreads + t]; b += remote[2 * kBlockThreads + t];
+            }
+        }
+        if (P.acc) P.acc[lpix] = make_double4(r, g, b, 0.0);
+        const double wgt = 1.0 / (double)P.samples;                                  // tracer.cl:837, 1184-1187
+        const size_t opix = (size_t)(P.out_row ? P.out_row[px.ly] : px.ly) * W + px.lx;
+        if (P.out_f32) reinterpret_cast<float4*>(P.out)[opix] = make_float4((float)(r * wgt), (float)(g * wgt), (float)(b * wgt), 1.0f);
+        else reinterpret_cast<double4*>(P.out)[opix] = make_double4(r * wgt, g * wgt, b * wgt, 1.0);
+    }
+    if (cluster_size > 1) cluster.sync();          // remote shared memory stays alive until the first block has read it
 }
 
-// Sums the per-slice partials in slice order (deterministic) and applies the 1/samples weight.
-// With `acc` the sums are first added to a running per-pixel accumulator (progressive rendering:
-// several sample ranges, each its own launch).
-__global__ void resolve_slices_kernel(const double4* __restrict__ partial, double4* __restrict__ acc, double4* __restrict__ out,
-                                      int pixels, int slices, int samples) {
+// RGBA double -> float (the reference's frontend keeps float64 but its .raw writer and canvas store float32-range data,
+// internal/app/raw/writer.go:11-35): halves the readback of a caller that only wants single precision.
+__global__ void f32_kernel(const double4* __restrict__ in, float4* __restrict__ out, int pixels) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels) return;
-    double r = 0.0, g = 0.0, b = 0.0;
-    if (acc) { double4 a = acc[i]; r = a.x; g = a.y; b = a.z; }
-    for (int s = 0; s < slices; ++s) {
-        double4 p = partial[(size_t)s * pixels + i];
-        r += p.x; g += p.y; b += p.z;
-    }
-    if (acc) acc[i] = make_double4(r, g, b, 0.0);
-    const double wgt = 1.0 / (double)samples;
-    out[i] = make_double4(r * wgt, g * wgt, b * wgt, 1.0);
+    const double4 c = in[i];
+    out[i] = make_float4((float)c.x, (float)c.y, (float)c.z, (float)c.w);
 }
 
 // Frontend tone step on the device (reference internal/app/tracer/pathtracer.go:42-59: no gamma,
@@ -980,6 +1037,20 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ out, 
         for (int k = 0; k < 16; ++k) {
             a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
             a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// The same for the FP64 pipe (the fp64 mode's roofline): 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* __restrict__ out, int iters) {
+    double a0 = threadIdx.x * 1e-6, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double b = 0.999999, c = 1e-7 * (blockIdx.x + 1);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));

@@ -57,8 +57,11 @@ void set_err(char* err, int errlen, const char* msg) {
 // ---- flattened scene (host copy), templated on the arithmetic type -----------------------------
 template <typename R> struct HostScene {
     ptk::DObjHot<R> hot[ptk::kMaxObjects];
-    ptk::DRun runs[ptk::kMaxObjects];
-    int n_runs = 0;
+    ptk::DFast<R> fast[ptk::kFastSlots];
+    int fast_n[4], fast_obj[ptk::kFastSlots];
+    int slow_obj[ptk::kMaxObjects], n_slow = 0;
+    int mesh_obj[ptk::kMaxObjects], n_mesh = 0;
+    int stack_need = 0;        // deepest deferred-child stack any mesh of the scene can need
     std::vector<ptk::DObjShade<R>> shade;
     std::vector<ptk::DMesh<R>> mesh;              // one per object
     std::vector<R> lens;       // sunflower lens points, 2 per sample (empty without depth of field)
@@ -382,6 +385,7 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
     }
     if (builder.stack_need > ptk::kWideStack) fail("object %d: rebuilt BVH needs %d traversal stack entries (limit %d)", obj_index, builder.stack_need, ptk::kWideStack);
     out.mesh_depth = std::max(out.mesh_depth, builder.wide_depth);
+    out.stack_need = std::max(out.stack_need, builder.stack_need);
     R lo[3], hi[3];
     padded<R>(root_box, lo, hi);
     for (int a = 0; a < 3; ++a) { m.root_lo[a] = lo[a]; m.root_hi[a] = hi[a]; }
@@ -421,9 +425,6 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
         }
         h.node_begin = h.node_end = 0;
         if (h.type == 2) { h.aux[0] = R(s.min_y); h.aux[1] = R(s.max_y); }
-        if (h.type == 1 && s.inverse[1] == 0.0 && s.inverse[2] == 0.0 && s.inverse[4] == 0.0 && s.inverse[6] == 0.0 &&
-            s.inverse[8] == 0.0 && s.inverse[9] == 0.0)
-            h.type = 5;                                         // intersection-loop fast path; o.type stays 1 for shading
         ptk::DMesh<R> m;
         std::memset(&m, 0, sizeof m);
         m.bvh_root = -1;
@@ -440,11 +441,49 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
         out.mesh.push_back(m);
         out.shade.push_back(o);
     }
-    // runs of consecutive same-type objects (order preserved)
-    out.n_runs = 0;
+    // Intersection order.  Planes and spheres whose `inverse` is a similarity (uniform scale, any rotation: the unit
+    // sphere is then a world-space sphere of radius 1/s around the transform's translation) take the kernel's unrolled
+    // fast slots -- three runs "spheres, planes, spheres" filled greedily in scene order, so fast objects keep their
+    // relative order; other analytic objects take the slow loop; groups with triangles the mesh walk.
+    out.n_slow = out.n_mesh = 0;
+    for (int k = 0; k < 4; ++k) out.fast_n[k] = 0;
+    for (int k = 0; k < ptk::kFastSlots; ++k) { out.fast_obj[k] = -1; out.fast[k] = ptk::DFast<R>{R(0), R(0), R(0), R(0)}; }
+    const int run_begin[3] = {0, ptk::kFastA, ptk::kFastA + ptk::kFastB}, run_cap[3] = {ptk::kFastA, ptk::kFastB, ptk::kFastC};
+    int run = 0;                                                     // run currently being filled (never goes back)
     for (int i = 0; i < job.n_objects; ++i) {
-        if (out.n_runs > 0 && out.runs[out.n_runs - 1].type == out.hot[i].type) { out.runs[out.n_runs - 1].end = i + 1; continue; }
-        out.runs[out.n_runs++] = ptk::DRun{out.hot[i].type, i, i + 1, 0};
+        const ptw_object& s = objs[i];
+        const int type = out.hot[i].type;
+        if (type == 4) { if (out.mesh[size_t(i)].bvh_root >= 0) out.mesh_obj[out.n_mesh++] = i; continue; }
+        if (type < 0 || type > 3) continue;                          // unknown type: never hit (tracer.cl:549-597 has no branch for it)
+        ptk::DFast<R> rec{R(0), R(0), R(0), R(0)};
+        int want = -1;                                               // 0: a sphere run, 1: the plane run
+        if (type == 0) {
+            rec = ptk::DFast<R>{R(s.inverse[4]), R(s.inverse[5]), R(s.inverse[6]), R(s.inverse[7])};
+            want = 1;
+        } else if (type == 1) {
+            const double* m = s.inverse;
+            const double s2 = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+            auto near = [&](double v, double target) { return std::fabs(v - target) <= 1e-12 * s2; };
+            const bool similarity = s2 > 0.0 && std::isfinite(s2) && near(m[4] * m[4] + m[5] * m[5] + m[6] * m[6], s2) &&
+                                    near(m[8] * m[8] + m[9] * m[9] + m[10] * m[10], s2) && near(m[0] * m[4] + m[1] * m[5] + m[2] * m[6], 0.0) &&
+                                    near(m[0] * m[8] + m[1] * m[9] + m[2] * m[10], 0.0) && near(m[4] * m[8] + m[5] * m[9] + m[6] * m[10], 0.0) &&
+                                    m[12] == 0.0 && m[13] == 0.0 && m[14] == 0.0 && m[15] == 1.0;
+            if (similarity) {
+                // centre = transform * (0,0,0,1) = -A^-1 t, taken from `inverse` itself so the two stay consistent: c = -(A^T t) / s^2
+                const double cx = -(m[0] * m[3] + m[4] * m[7] + m[8] * m[11]) / s2, cy = -(m[1] * m[3] + m[5] * m[7] + m[9] * m[11]) / s2,
+                             cz = -(m[2] * m[3] + m[6] * m[7] + m[10] * m[11]) / s2;
+                rec = ptk::DFast<R>{R(cx), R(cy), R(cz), R(1.0 / s2)};
+                want = 0;
+            }
+        }
+        int slot = -1;
+        if (want == 1 && run <= 1 && out.fast_n[1] < run_cap[1]) { run = 1; slot = run_begin[1] + out.fast_n[1]++; }
+        else if (want == 0) {
+            if (run == 0 && out.fast_n[0] < run_cap[0]) slot = run_begin[0] + out.fast_n[0]++;
+            else if (out.fast_n[2] < run_cap[2]) { run = 2; slot = run_begin[2] + out.fast_n[2]++; }
+        }
+        if (slot >= 0) { out.fast[slot] = rec; out.fast_obj[slot] = i; }
+        else out.slow_obj[out.n_slow++] = i;
     }
     const auto* cam = static_cast<const ptw_camera*>(job.camera);
     out.cam.pixel_size = R(cam->pixel_size); out.cam.half_width = R(cam->half_width); out.cam.half_height = R(cam->half_height);
@@ -482,18 +521,28 @@ struct DeviceState {
     void* wide = nullptr;
     void* tri_test = nullptr; void* tri_shade = nullptr; void* tri_info = nullptr;
     void* tex[3] = {nullptr, nullptr, nullptr};
-    double* seeds = nullptr;
-    int* row_map = nullptr;
-    double* out = nullptr;          // rows*W*4
-    double* partial = nullptr;      // slices*rows*W*4 per-slice sums (slices > 1 or progressive)
+    double* seeds = nullptr;        // rows*W: the seeds of the rows this device owns
+    int* row_map = nullptr;         // local row -> frame row
+    int* out_row = nullptr;         // local row -> row of the buffer the kernel stores into (packed context rows / frame rows)
+    double* out = nullptr;          // rows*W*4: this device's packed rows (unused while the kernel stores into a gather / frame buffer)
     double* acc = nullptr;          // rows*W*4 running sums of a progressive render
     uchar4* rgba8 = nullptr;        // rows*W tone-mapped bytes (ptc_read_rgba8)
-    int slices = 1;
+    float4* f32 = nullptr;          // rows*W float RGBA (ptc_read_f32)
+    int slices = 1, cluster = 1;    // sample slices per pixel; CTAs per cluster (slices = slices_per_block * cluster)
     int sm_count = 0;
     float last_ms = 0.f;
 };
 
 }  // namespace
+
+// A whole-frame buffer on one device that kernels of several contexts -- other devices of this process, or other
+// processes through a CUDA IPC mapping -- store their pixels into directly (the gather fused into the trace kernel).
+struct ptc_frame {
+    int device = 0, width = 0, height = 0, format = PTC_FRAME_F64;
+    void* data = nullptr;
+    bool owner = false;         // false: `data` is an IPC mapping of another process's allocation
+    size_t bytes() const { return size_t(width) * height * (format == PTC_FRAME_F32 ? 16 : 32); }
+};
 
 struct ptc_context {
     int width = 0, height = 0, samples = 0, precision = PTC_FP32, rng_mode = PTC_RNG_PARITY;
@@ -504,19 +553,23 @@ struct ptc_context {
     HostScene<float> scene32;
     HostScene<double> scene64;
     int tex_w[3] = {0, 0, 0}, tex_h[3] = {0, 0, 0}, tex_layers[3] = {0, 0, 0};
-    double* gather = nullptr;                    // on dev[0]: packed rows of the whole context (n_devices > 1)
-    bool peer_ok = false;
+    double* gather = nullptr;                    // on dev[0]: packed rows of the whole context (n_devices > 1), written by every device's kernel
+    bool peer_ok = false;                        // every device can store into dev[0]'s memory
+    ptc_frame* frame = nullptr;                  // attached frame (ptc_set_frame): kernels store there, by frame row
+    int nee = 0, caps = 0;                       // ptc_job.features
     ptc_stats stats{};
 };
 
 namespace {
 
 // Device memory for single-GPU contexts comes from a per-device stream-ordered pool that keeps its
-// blocks between calls (release threshold = max): a render no longer pays cudaMalloc/cudaFree --
-// the latter synchronises the device and was measured to stall for up to 1.3 s inside a process
-// that also hosts another CUDA allocator.  Multi-GPU contexts use plain cudaMalloc so the peer
-// copies of the gather need no per-pool access grants.  The pool table is the only global state;
-// it is mutex-protected and holds driver handles only.  ptc_trim() returns the memory.
+// blocks between calls: a render no longer pays cudaMalloc/cudaFree -- the latter synchronises the
+// device and was measured to stall for up to 1.3 s inside a process that also hosts another CUDA
+// allocator.  What the pool retains is bounded (kPoolKeepBytes: a 4K fp64 frame with its seeds and a
+// mesh scene fit); anything above goes back to the driver when the context closes.  Multi-GPU contexts
+// use plain cudaMalloc so peer stores need no per-pool access grants.  The pool table is the only global
+// state; it is mutex-protected and holds driver handles only.  ptc_trim() returns the rest.
+constexpr uint64_t kPoolKeepBytes = 768ull << 20;
 std::mutex g_pool_mutex;
 cudaMemPool_t g_pools[64] = {};
 
@@ -532,7 +585,7 @@ cudaMemPool_t pool_for(int device) {
         props.location.id = device;
         cudaMemPool_t pool = nullptr;
         if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        uint64_t keep = UINT64_MAX;
+        uint64_t keep = kPoolKeepBytes;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         g_pools[device] = pool;
     }
@@ -555,7 +608,7 @@ template <typename T> void* upload(DeviceState& d, const std::vector<T>& v, int6
     return p;
 }
 
-template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const HostScene<R>& s, int64_t& h2d) {
+template <typename R> void upload_scene(DeviceState& d, const HostScene<R>& s, int64_t& h2d) {
     d.shade = upload(d, s.shade, h2d);
     d.lens = s.lens.empty() ? nullptr : upload(d, s.lens, h2d);
     d.node_lo = upload(d, s.node_lo, h2d);
@@ -566,15 +619,50 @@ template <typename R> void upload_scene(ptc_context& c, DeviceState& d, const Ho
     d.tri_test = upload(d, s.tri_test, h2d);
     d.tri_shade = upload(d, s.tri_shade, h2d);
     d.tri_info = upload(d, s.tri_info, h2d);
-    (void)c;
+}
+
+// Seeds of the rows a device owns, from the caller's full-frame array (one double per pixel, row-major): the rows
+// come in runs (scanline tiles) at a regular pitch, so one strided copy moves them; ragged layouts fall back to a
+// copy per run.  Only the owned rows cross PCIe (round 1 sent every device the whole frame).
+void upload_seeds(DeviceState& d, const double* seeds, int width, int64_t& h2d) {
+    const size_t row_bytes = size_t(width) * sizeof(double);
+    struct Run { int first, count; };
+    std::vector<Run> runs;
+    for (int r : d.rows) {
+        if (!runs.empty() && runs.back().first + runs.back().count == r) runs.back().count++;
+        else runs.push_back(Run{r, 1});
+    }
+    size_t regular = 0;                          // leading runs of equal length at a constant pitch
+    if (runs.size() >= 2) {
+        const int len = runs[0].count, pitch = runs[1].first - runs[0].first;
+        regular = 1;
+        while (regular < runs.size() && runs[regular].count == len && runs[regular].first - runs[regular - 1].first == pitch) ++regular;
+        if (regular >= 2)
+            CUDA_OK(cudaMemcpy2DAsync(d.seeds, size_t(len) * row_bytes, seeds + size_t(runs[0].first) * width, size_t(pitch) * row_bytes,
+                                      size_t(len) * row_bytes, regular, cudaMemcpyHostToDevice, d.stream));
+        else regular = 0;
+    }
+    size_t local = 0;
+    for (size_t k = 0; k < runs.size(); ++k) {
+        if (k >= regular)
+            CUDA_OK(cudaMemcpyAsync(d.seeds + local * width, seeds + size_t(runs[k].first) * width, size_t(runs[k].count) * row_bytes,
+                                    cudaMemcpyHostToDevice, d.stream));
+        local += size_t(runs[k].count);
+    }
+    h2d += int64_t(d.rows.size() * row_bytes);
 }
 
 template <typename R> ptk::Params<R> make_params(const ptc_context& c, const DeviceState& d, const HostScene<R>& s) {
     ptk::Params<R> P;
     std::memset(&P, 0, sizeof P);
     std::memcpy(P.hot, s.hot, sizeof P.hot);
-    std::memcpy(P.runs, s.runs, sizeof P.runs);
-    P.n_runs = s.n_runs;
+    std::memcpy(P.fast, s.fast, sizeof P.fast);
+    std::memcpy(P.fast_n, s.fast_n, sizeof P.fast_n);
+    std::memcpy(P.fast_obj, s.fast_obj, sizeof P.fast_obj);
+    std::memcpy(P.slow_obj, s.slow_obj, sizeof P.slow_obj);
+    std::memcpy(P.mesh_obj, s.mesh_obj, sizeof P.mesh_obj);
+    P.n_slow = s.n_slow; P.n_mesh = s.n_mesh;
+    P.stack_entries = (s.stack_need + 1) | 1;          // odd: the four groups of a warp push to different banks
     P.shade = static_cast<const ptk::DObjShade<R>*>(d.shade);
     P.lens = static_cast<const R*>(d.lens);
     P.n_objects = c.n_objects;
@@ -590,58 +678,67 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     for (int k = 0; k < 3; ++k) P.tex[k] = ptk::DTex{static_cast<const uchar4*>(d.tex[k]), c.tex_w[k], c.tex_h[k], c.tex_layers[k]};
     P.seeds = d.seeds;
     P.row_map = d.row_map;
-    P.out = d.out;
-    P.sample_begin = 0; P.sample_end = c.samples; P.raw_sums = 0;
+    P.sample_begin = 0; P.sample_end = c.samples;
     P.rows = int(d.rows.size());
     P.samples = c.samples;
     P.slices = d.slices;
+    P.slices_per_block = std::min(d.slices, ptk::kBlockWarps);
     P.pi = R(double(3.14159265359f));
     P.eps = R(0.0001);
+    P.nee = c.nee; P.caps = c.caps;
+    // where the pixels go: an attached frame (by frame row), the context's gather buffer on dev[0] (by position among
+    // the context's rows), or this device's own packed rows
+    if (c.frame) { P.out = c.frame->data; P.out_row = d.row_map; P.out_f32 = c.frame->format == PTC_FRAME_F32; }
+    else if (c.gather && c.peer_ok) { P.out = c.gather; P.out_row = d.out_row; }
+    else { P.out = d.out; P.out_row = nullptr; }
     return P;
 }
 
+template <typename K, typename R>
+void launch_kernel(K kernel, dim3 grid, dim3 block, size_t smem, int cluster, cudaStream_t stream, const ptk::Params<R>& P) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(cluster); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 1 : 0;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, P));
+}
+
 // Renders samples [begin, end) of every pixel this device owns.  accumulate == false: a full, self-contained
-// render (begin = 0, end = samples) whose weighted result lands in d.out.  accumulate == true: the sums are
-// added to the per-pixel accumulator d.acc (progressive rendering) and d.out = acc / samples.
+// render (begin = 0, end = samples).  accumulate == true: the sums are added to the per-pixel accumulator d.acc
+// (progressive rendering) and the stored pixel is acc / samples.  One launch either way: the slices of a pixel are
+// reduced inside the kernel (shared memory + the cluster's distributed shared memory).
 template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScene<R>& s, int begin, int end, bool accumulate) {
     const int rows = int(d.rows.size());
     if (rows == 0) return;
     const size_t pixels = size_t(rows) * size_t(c.width);
-    const bool use_partial = d.slices > 1 || accumulate;
-    if (use_partial && !d.partial) d.partial = static_cast<double*>(dmalloc(d, size_t(d.slices) * pixels * 4 * sizeof(double)));
     if (accumulate && !d.acc) {
         d.acc = static_cast<double*>(dmalloc(d, pixels * 4 * sizeof(double)));
         CUDA_OK(cudaMemsetAsync(d.acc, 0, pixels * 4 * sizeof(double), d.stream));
     }
     ptk::Params<R> P = make_params<R>(c, d, s);
     P.sample_begin = begin; P.sample_end = end;
-    P.raw_sums = accumulate ? 1 : 0;
-    P.out = use_partial ? d.partial : d.out;
+    P.acc = accumulate ? reinterpret_cast<double4*>(d.acc) : nullptr;
     const int tiles_x = (c.width + ptk::kTileW - 1) / ptk::kTileW;
     const int tiles_y = (rows + ptk::kTileH - 1) / ptk::kTileH;
-    const long long warps = (long long)tiles_x * tiles_y;
-    bool meshes = false;
-    for (int i = 0; i < c.n_objects; ++i) meshes = meshes || s.mesh[size_t(i)].bvh_root >= 0;
+    const long long tiles = (long long)tiles_x * tiles_y;
+    const int tiles_per_block = ptk::kBlockWarps / P.slices_per_block;
+    const bool meshes = s.n_mesh > 0;
     const bool fast = c.rng_mode == PTC_RNG_FAST;
-    const int warps_per_block = ptk::kBlockThreads / 32;
-    dim3 grid((unsigned)((warps + warps_per_block - 1) / warps_per_block), (unsigned)d.slices, 1);
+    dim3 grid((unsigned)((tiles + tiles_per_block - 1) / tiles_per_block * d.cluster), 1, 1);
     dim3 block(ptk::kBlockThreads, 1, 1);
+    const size_t smem = meshes ? size_t(ptk::kBlockThreads / ptk::kWide) * size_t(P.stack_entries) * sizeof(int2) : 0;
     if (meshes) {
-        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, true><<<grid, block, 0, d.stream>>>(P);
-        else ptk::trace_kernel<R, ptk::RNG_PARITY, true><<<grid, block, 0, d.stream>>>(P);
+        if (fast) launch_kernel(ptk::trace_kernel<R, ptk::RNG_FAST, true>, grid, block, smem, d.cluster, d.stream, P);
+        else launch_kernel(ptk::trace_kernel<R, ptk::RNG_PARITY, true>, grid, block, smem, d.cluster, d.stream, P);
     } else {
-        if (fast) ptk::trace_kernel<R, ptk::RNG_FAST, false><<<grid, block, 0, d.stream>>>(P);
-        else ptk::trace_kernel<R, ptk::RNG_PARITY, false><<<grid, block, 0, d.stream>>>(P);
+        if (fast) launch_kernel(ptk::trace_kernel<R, ptk::RNG_FAST, false>, grid, block, smem, d.cluster, d.stream, P);
+        else launch_kernel(ptk::trace_kernel<R, ptk::RNG_PARITY, false>, grid, block, smem, d.cluster, d.stream, P);
     }
     CUDA_OK(cudaGetLastError());
     c.stats.kernel_launches++;
-    if (use_partial) {
-        ptk::resolve_slices_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, d.stream>>>(
-            reinterpret_cast<const double4*>(d.partial), accumulate ? reinterpret_cast<double4*>(d.acc) : nullptr,
-            reinterpret_cast<double4*>(d.out), int(pixels), d.slices, c.samples);
-        CUDA_OK(cudaGetLastError());
-        c.stats.kernel_launches++;
-    }
 }
 
 void validate(const ptc_job& j) {
@@ -663,7 +760,8 @@ void validate(const ptc_job& j) {
         if (j.tex[k] && (j.tex_w[k] <= 0 || j.tex_h[k] <= 0 || j.tex_layers[k] <= 0)) fail("texture class %d has a non-positive size", k);
     if (j.shard_count > 1 && (j.shard_index < 0 || j.shard_index >= j.shard_count)) fail("shard_index %d outside [0,%d)", j.shard_index, j.shard_count);
     if (j.n_devices < 0 || (j.n_devices > 0 && !j.devices)) fail("bad device list");
-    for (int k = 0; k < 8; ++k) if (j.reserved[k] != 0) fail("ptc_job.reserved must be zero");
+    if (j.features & ~(PTC_FEATURE_NEE | PTC_FEATURE_CYLINDER_CAPS)) fail("unknown bits in ptc_job.features: 0x%x", j.features);
+    for (int k = 0; k < 7; ++k) if (j.reserved[k] != 0) fail("ptc_job.reserved must be zero");
 }
 
 void destroy(ptc_context* c) {
@@ -683,6 +781,23 @@ void destroy(ptc_context* c) {
     delete c;
 }
 
+// Sample slices per pixel for a device that owns `px` pixels.  Small frames cannot fill 148 SMs with one thread
+// per pixel, and blocks that live for the whole frame leave a long tail (measured on B200: a 1/8-frame shard ran
+// 36.3 ms with 1 slice, 29.3 ms with 32), so each pixel's samples are split into interleaved slices until there are
+// ~16x the resident thread capacity in total threads; scenes with meshes, whose pixels differ several-fold in cost,
+// get 8x finer slices (teapot 2.83 -> 3.12 Gpaths/s from 4 to 32 slices).  A power of two, at most
+// kBlockWarps * kMaxCluster = 32: all slices of a pixel sit in one thread-block cluster, which reduces them.
+int plan_slices(long long px, int sm_count, bool meshes, int samples) {
+    const long long want = (long long)sm_count * 2048 * (meshes ? 128 : 16);
+    long long sl = px ? (want + px - 1) / px : 1;
+    if (const char* ov = std::getenv("PTC_SLICES")) sl = std::atoll(ov);    // tuning override
+    const long long cap = std::min<long long>(samples, ptk::kBlockWarps * ptk::kMaxCluster);
+    if (sl > cap) sl = cap;
+    int pow2 = 1;
+    while (2ll * pow2 <= sl) pow2 *= 2;
+    return pow2;
+}
+
 ptc_context* open_impl(const ptc_job& job) {
     validate(job);
     auto t0 = Clock::now();
@@ -696,6 +811,8 @@ ptc_context* open_impl(const ptc_job& job) {
     const auto* cam = static_cast<const ptw_camera*>(job.camera);
     c.width = cam->width; c.height = cam->height; c.samples = job.samples;
     c.precision = job.precision; c.rng_mode = job.rng_mode; c.n_objects = job.n_objects;
+    c.nee = (job.features & PTC_FEATURE_NEE) ? 1 : 0;
+    c.caps = (job.features & PTC_FEATURE_CYLINDER_CAPS) ? 1 : 0;
     c.shard_count = job.shard_count > 1 ? job.shard_count : 1;
     c.shard_index = job.shard_count > 1 ? job.shard_index : 0;
     c.rows_per_tile = job.rows_per_tile > 0 ? job.rows_per_tile : 4;
@@ -718,18 +835,22 @@ ptc_context* open_impl(const ptc_job& job) {
     c.dev.resize(size_t(nd));
     const int n_tiles = (c.height + c.rows_per_tile - 1) / c.rows_per_tile;
     int local_tile = 0;
+    std::vector<std::vector<int>> out_rows{size_t(nd)};          // per device: position of each of its rows among the context's rows
     for (int k = 0; k < n_tiles; ++k) {
         if (k % c.shard_count != c.shard_index) continue;
         DeviceState& d = c.dev[size_t(local_tile % nd)];
-        for (int r = k * c.rows_per_tile; r < (k + 1) * c.rows_per_tile && r < c.height; ++r) { d.rows.push_back(r); c.rows.push_back(r); }
+        for (int r = k * c.rows_per_tile; r < (k + 1) * c.rows_per_tile && r < c.height; ++r) {
+            out_rows[size_t(local_tile % nd)].push_back(int(c.rows.size()));
+            d.rows.push_back(r); c.rows.push_back(r);
+        }
         ++local_tile;
     }
 
     if (c.precision == PTC_FP64) flatten<double>(job, c.scene64);
     else flatten<float>(job, c.scene32);
+    const bool meshes = (c.precision == PTC_FP64 ? c.scene64.n_mesh : c.scene32.n_mesh) > 0;
 
     int64_t h2d = 0;
-    const size_t frame_px = size_t(c.width) * c.height;
     for (int i = 0; i < nd; ++i) {
         DeviceState& d = c.dev[size_t(i)];
         d.device = devices[size_t(i)];
@@ -743,8 +864,8 @@ ptc_context* open_impl(const ptc_job& job) {
         if (nd == 1) d.pool = pool_for(d.device);
         CUDA_OK(cudaEventCreate(&d.ev0));
         CUDA_OK(cudaEventCreate(&d.ev1));
-        if (c.precision == PTC_FP64) upload_scene<double>(c, d, c.scene64, h2d);
-        else upload_scene<float>(c, d, c.scene32, h2d);
+        if (c.precision == PTC_FP64) upload_scene<double>(d, c.scene64, h2d);
+        else upload_scene<float>(d, c.scene32, h2d);
         for (int k = 0; k < 3; ++k) {
             if (!job.tex[k]) continue;
             size_t bytes = size_t(c.tex_w[k]) * c.tex_h[k] * c.tex_layers[k] * 4;
@@ -752,44 +873,32 @@ ptc_context* open_impl(const ptc_job& job) {
             CUDA_OK(cudaMemcpyAsync(d.tex[k], job.tex[k], bytes, cudaMemcpyHostToDevice, d.stream));
             h2d += int64_t(bytes);
         }
-        d.seeds = static_cast<double*>(dmalloc(d, frame_px * sizeof(double)));
-        CUDA_OK(cudaMemcpyAsync(d.seeds, job.seeds, frame_px * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-        h2d += int64_t(frame_px * sizeof(double));
-        d.row_map = static_cast<int*>(upload(d, d.rows, h2d));
         const size_t px = d.rows.size() * size_t(c.width);
+        d.seeds = static_cast<double*>(dmalloc(d, px * sizeof(double)));
+        upload_seeds(d, job.seeds, c.width, h2d);
+        d.row_map = static_cast<int*>(upload(d, d.rows, h2d));
+        d.out_row = nd > 1 ? static_cast<int*>(upload(d, out_rows[size_t(i)], h2d)) : nullptr;
         d.out = static_cast<double*>(dmalloc(d, px * 4 * sizeof(double)));
-        // Small frames cannot fill 148 SMs with one thread per pixel: split each pixel's samples
-        // into interleaved slices until there are ~4 resident-warp sets of work.
-        // Measured on B200 (tools/slices_time.py): blocks that live for the whole frame leave a long
-        // tail (a 1/8-frame shard ran 36.3 ms with 1 slice, 29.3 ms with 32), so aim for ~16x the
-        // resident thread capacity in total threads.
-        // Scenes with meshes have very uneven pixels (a warp on the mesh runs several times longer than one on a
-        // wall): finer slices even the load out -- measured at 1280x960@256: teapot 2.83 Gpaths/s with 4 slices,
-        // 3.12 with 32; cubemap+gopher 4.84 -> 6.68 -- so they get 8x the thread count of analytic scenes.
-        bool meshes = false;
-        for (int k = 0; k < c.n_objects; ++k)
-            meshes = meshes || (c.precision == PTC_FP64 ? c.scene64.mesh[size_t(k)].bvh_root >= 0 : c.scene32.mesh[size_t(k)].bvh_root >= 0);
-        const long long want = (long long)d.sm_count * 2048 * (meshes ? 128 : 16);
-        long long sl = px ? (want + (long long)px - 1) / (long long)px : 1;
-        long long cap = meshes ? 64 : 32;
-        if (const char* ov = std::getenv("PTC_SLICES")) { sl = std::atoll(ov); cap = 4096; }    // tuning override
-        if (sl > c.samples) sl = c.samples;
-        if (sl > cap) sl = cap;
-        if (sl < 1) sl = 1;
-        d.slices = int(sl);
+        d.slices = plan_slices((long long)px, d.sm_count, meshes, c.samples);
+        d.cluster = std::max(1, d.slices / ptk::kBlockWarps);
     }
     if (nd > 1) {
+        // Every device's kernel stores its pixels straight into one buffer on dev[0] (NVLink peer stores from the
+        // kernel epilogue), so the read is a single D2H.  That needs peer access FROM each device TO dev[0].
         DeviceState& d0 = c.dev[0];
-        CUDA_OK(cudaSetDevice(d0.device));
-        c.gather = static_cast<double*>(dmalloc(d0, c.rows.size() * size_t(c.width) * 4 * sizeof(double)));
         c.peer_ok = true;
         for (int i = 1; i < nd; ++i) {
             int can = 0;
-            CUDA_OK(cudaDeviceCanAccessPeer(&can, d0.device, c.dev[size_t(i)].device));
-            if (!can) { c.peer_ok = false; continue; }
-            cudaError_t pe = cudaDeviceEnablePeerAccess(c.dev[size_t(i)].device, 0);
+            CUDA_OK(cudaDeviceCanAccessPeer(&can, c.dev[size_t(i)].device, d0.device));
+            if (!can) { c.peer_ok = false; break; }
+            CUDA_OK(cudaSetDevice(c.dev[size_t(i)].device));
+            cudaError_t pe = cudaDeviceEnablePeerAccess(d0.device, 0);
             if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) c.peer_ok = false;
             cudaGetLastError();
+        }
+        if (c.peer_ok) {
+            CUDA_OK(cudaSetDevice(d0.device));
+            c.gather = static_cast<double*>(dmalloc(d0, c.rows.size() * size_t(c.width) * 4 * sizeof(double)));
         }
     }
     for (DeviceState& d : c.dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
@@ -820,23 +929,25 @@ void trace_impl(ptc_context& c, int begin, int end, bool accumulate) {
     c.stats.kernel_ms = worst;
 }
 
-// Position of frame row `r` inside the packed row list of the context.
+// The double frame of the context's rows on dev[0] when every device stored into the gather buffer; else NULL.
+const double* gathered(const ptc_context& c) { return (c.dev.size() > 1 && c.gather && c.peer_ok && !c.frame) ? c.gather : nullptr; }
+
 void read_impl(ptc_context& c, double* out) {
     auto t0 = Clock::now();
+    if (c.frame) fail("ptc_read: the context renders into an attached frame; read it with ptc_frame_read");
     const size_t row_bytes = size_t(c.width) * 4 * sizeof(double);
     c.stats.d2h_bytes = 0; c.stats.p2p_bytes = 0;
     const int nd = int(c.dev.size());
-    if (nd == 1) {
+    if (nd == 1 || gathered(c)) {
         DeviceState& d = c.dev[0];
         CUDA_OK(cudaSetDevice(d.device));
-        CUDA_OK(cudaMemcpyAsync(out, d.out, d.rows.size() * row_bytes, cudaMemcpyDeviceToHost, d.stream));
+        CUDA_OK(cudaMemcpyAsync(out, nd == 1 ? d.out : c.gather, c.rows.size() * row_bytes, cudaMemcpyDeviceToHost, d.stream));
         CUDA_OK(cudaStreamSynchronize(d.stream));
-        c.stats.d2h_bytes = int64_t(d.rows.size() * row_bytes);
+        c.stats.d2h_bytes = int64_t(c.rows.size() * row_bytes);
+        if (nd > 1) c.stats.p2p_bytes = int64_t((c.rows.size() - d.rows.size()) * row_bytes);     // stored over NVLink by the kernels
     } else {
-        // Device i owns local tiles i, i+nd, i+2nd, ...: one strided 2-D copy per device places them
-        // in the packed frame (tile pitch nd*tile_bytes).  With peer access the copies run
-        // device->device over NVLink into dev[0] and a single D2H follows; otherwise each device
-        // copies straight into the host buffer.
+        // No peer access: device i owns local tiles i, i+nd, i+2nd, ...: one strided 2-D copy per device places
+        // them in the packed host frame (tile pitch nd*tile_bytes).
         const size_t tile_bytes = row_bytes * size_t(c.rows_per_tile);
         for (int i = 0; i < nd; ++i) {
             DeviceState& d = c.dev[size_t(i)];
@@ -844,23 +955,16 @@ void read_impl(ptc_context& c, double* out) {
             CUDA_OK(cudaSetDevice(d.device));
             const size_t full_tiles = d.rows.size() / size_t(c.rows_per_tile);
             const size_t tail_rows = d.rows.size() % size_t(c.rows_per_tile);
-            char* dst_base = c.peer_ok ? reinterpret_cast<char*>(c.gather) : reinterpret_cast<char*>(out);
-            const cudaMemcpyKind kind = c.peer_ok ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            char* dst_base = reinterpret_cast<char*>(out);
             if (full_tiles)
-                CUDA_OK(cudaMemcpy2DAsync(dst_base + size_t(i) * tile_bytes, size_t(nd) * tile_bytes, d.out, tile_bytes, tile_bytes, full_tiles, kind, d.stream));
+                CUDA_OK(cudaMemcpy2DAsync(dst_base + size_t(i) * tile_bytes, size_t(nd) * tile_bytes, d.out, tile_bytes, tile_bytes, full_tiles,
+                                          cudaMemcpyDeviceToHost, d.stream));
             if (tail_rows)
                 CUDA_OK(cudaMemcpyAsync(dst_base + (full_tiles * size_t(nd) + size_t(i)) * tile_bytes, reinterpret_cast<char*>(d.out) + full_tiles * tile_bytes,
-                                        tail_rows * row_bytes, kind, d.stream));
-            if (c.peer_ok) c.stats.p2p_bytes += int64_t(d.rows.size() * row_bytes); else c.stats.d2h_bytes += int64_t(d.rows.size() * row_bytes);
+                                        tail_rows * row_bytes, cudaMemcpyDeviceToHost, d.stream));
+            c.stats.d2h_bytes += int64_t(d.rows.size() * row_bytes);
         }
         for (DeviceState& d : c.dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
-        if (c.peer_ok) {
-            DeviceState& d0 = c.dev[0];
-            CUDA_OK(cudaSetDevice(d0.device));
-            CUDA_OK(cudaMemcpyAsync(out, c.gather, c.rows.size() * row_bytes, cudaMemcpyDeviceToHost, d0.stream));
-            CUDA_OK(cudaStreamSynchronize(d0.stream));
-            c.stats.d2h_bytes = int64_t(c.rows.size() * row_bytes);
-        }
     }
     c.stats.read_ms = ms_since(t0);
 }
@@ -880,7 +984,7 @@ template <typename F> int guarded(char* err, int errlen, F&& f) {
 
 extern "C" {
 
-const char* ptc_version(void) { return "libptcuda 0.1 (sm_100a)"; }
+const char* ptc_version(void) { return "libptcuda 0.2 (sm_100a) kernel " PTK_KERNEL_VERSION; }
 
 int ptc_device_count(void) {
     int n = 0;
@@ -935,39 +1039,67 @@ int ptc_reset(ptc_context* ctx, char* err, int errlen) {
     });
 }
 
-int ptc_read_rgba8(ptc_context* ctx, uint8_t* out_rgba8, char* err, int errlen) {
-    return guarded(err, errlen, [&] {
-        if (!ctx || !out_rgba8) fail("ptc_read_rgba8: NULL argument");
-        ptc_context& c = *ctx;
-        auto t0 = Clock::now();
-        const int nd = int(c.dev.size());
-        const size_t row_bytes = size_t(c.width) * 4;
-        const size_t tile_bytes = row_bytes * size_t(c.rows_per_tile);
-        c.stats.d2h_bytes = 0; c.stats.p2p_bytes = 0;
+// ptc_read_rgba8 / ptc_read_f32: convert on the device that holds the pixels, read back the narrow format.
+// bytes_px = 4 (RGBA8, the frontend's tone step) or 16 (float RGBA).
+static void read_converted(ptc_context& c, void* out, size_t bytes_px) {
+    auto t0 = Clock::now();
+    if (c.frame) fail("the context renders into an attached frame; read it with ptc_frame_read");
+    const int nd = int(c.dev.size());
+    const size_t row_bytes = size_t(c.width) * bytes_px;
+    const size_t tile_bytes = row_bytes * size_t(c.rows_per_tile);
+    c.stats.d2h_bytes = 0; c.stats.p2p_bytes = 0;
+    auto convert = [&](DeviceState& d, const double* src, size_t pixels) -> void* {
+        void*& dst = bytes_px == 4 ? reinterpret_cast<void*&>(d.rgba8) : reinterpret_cast<void*&>(d.f32);
+        if (!dst) dst = dmalloc(d, std::max<size_t>(pixels, c.rows.size() * size_t(c.width)) * bytes_px);
+        const unsigned blocks = (unsigned)((pixels + 255) / 256);
+        if (bytes_px == 4) ptk::rgba8_kernel<<<blocks, 256, 0, d.stream>>>(reinterpret_cast<const double4*>(src), static_cast<uchar4*>(dst), int(pixels));
+        else ptk::f32_kernel<<<blocks, 256, 0, d.stream>>>(reinterpret_cast<const double4*>(src), static_cast<float4*>(dst), int(pixels));
+        CUDA_OK(cudaGetLastError());
+        c.stats.kernel_launches++;
+        return dst;
+    };
+    if (nd == 1 || gathered(c)) {
+        DeviceState& d = c.dev[0];
+        if (c.rows.empty()) { c.stats.read_ms = ms_since(t0); return; }
+        CUDA_OK(cudaSetDevice(d.device));
+        const size_t pixels = c.rows.size() * size_t(c.width);
+        void* dst = convert(d, nd == 1 ? d.out : c.gather, pixels);
+        CUDA_OK(cudaMemcpyAsync(out, dst, pixels * bytes_px, cudaMemcpyDeviceToHost, d.stream));
+        CUDA_OK(cudaStreamSynchronize(d.stream));
+        c.stats.d2h_bytes = int64_t(pixels * bytes_px);
+    } else {
         for (int i = 0; i < nd; ++i) {
             DeviceState& d = c.dev[size_t(i)];
             if (d.rows.empty()) continue;
             CUDA_OK(cudaSetDevice(d.device));
             const size_t pixels = d.rows.size() * size_t(c.width);
-            if (!d.rgba8) d.rgba8 = static_cast<uchar4*>(dmalloc(d, pixels * 4));
-            ptk::rgba8_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, d.stream>>>(reinterpret_cast<const double4*>(d.out), d.rgba8, int(pixels));
-            CUDA_OK(cudaGetLastError());
-            c.stats.kernel_launches++;
-            if (nd == 1) {
-                CUDA_OK(cudaMemcpyAsync(out_rgba8, d.rgba8, pixels * 4, cudaMemcpyDeviceToHost, d.stream));
-            } else {   // device i owns local tiles i, i+nd, ...: strided copy straight into the packed host frame
-                const size_t full_tiles = d.rows.size() / size_t(c.rows_per_tile), tail_rows = d.rows.size() % size_t(c.rows_per_tile);
-                if (full_tiles)
-                    CUDA_OK(cudaMemcpy2DAsync(out_rgba8 + size_t(i) * tile_bytes, size_t(nd) * tile_bytes, d.rgba8, tile_bytes, tile_bytes, full_tiles,
-                                              cudaMemcpyDeviceToHost, d.stream));
-                if (tail_rows)
-                    CUDA_OK(cudaMemcpyAsync(out_rgba8 + (full_tiles * size_t(nd) + size_t(i)) * tile_bytes, reinterpret_cast<uint8_t*>(d.rgba8) + full_tiles * tile_bytes,
-                                            tail_rows * row_bytes, cudaMemcpyDeviceToHost, d.stream));
-            }
-            c.stats.d2h_bytes += int64_t(pixels * 4);
+            char* dst = static_cast<char*>(convert(d, d.out, pixels));
+            // device i owns local tiles i, i+nd, ...: strided copy straight into the packed host frame
+            const size_t full_tiles = d.rows.size() / size_t(c.rows_per_tile), tail_rows = d.rows.size() % size_t(c.rows_per_tile);
+            char* o = static_cast<char*>(out);
+            if (full_tiles)
+                CUDA_OK(cudaMemcpy2DAsync(o + size_t(i) * tile_bytes, size_t(nd) * tile_bytes, dst, tile_bytes, tile_bytes, full_tiles, cudaMemcpyDeviceToHost, d.stream));
+            if (tail_rows)
+                CUDA_OK(cudaMemcpyAsync(o + (full_tiles * size_t(nd) + size_t(i)) * tile_bytes, dst + full_tiles * tile_bytes, tail_rows * row_bytes,
+                                        cudaMemcpyDeviceToHost, d.stream));
+            c.stats.d2h_bytes += int64_t(pixels * bytes_px);
         }
         for (DeviceState& d : c.dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
-        c.stats.read_ms = ms_since(t0);
+    }
+    c.stats.read_ms = ms_since(t0);
+}
+
+int ptc_read_rgba8(ptc_context* ctx, uint8_t* out_rgba8, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx || !out_rgba8) fail("ptc_read_rgba8: NULL argument");
+        read_converted(*ctx, out_rgba8, 4);
+    });
+}
+
+int ptc_read_f32(ptc_context* ctx, float* out_rgba_f32, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx || !out_rgba_f32) fail("ptc_read_f32: NULL argument");
+        read_converted(*ctx, out_rgba_f32, 16);
     });
 }
 
@@ -989,20 +1121,114 @@ void ptc_close(ptc_context* ctx) { destroy(ctx); }
 int ptc_set_seeds(ptc_context* ctx, const double* seeds, char* err, int errlen) {
     return guarded(err, errlen, [&] {
         if (!ctx || !seeds) fail("ptc_set_seeds: NULL argument");
-        const size_t bytes = size_t(ctx->width) * ctx->height * sizeof(double);
+        int64_t h2d = 0;
         for (DeviceState& d : ctx->dev) {
             CUDA_OK(cudaSetDevice(d.device));
-            CUDA_OK(cudaMemcpyAsync(d.seeds, seeds, bytes, cudaMemcpyHostToDevice, d.stream));
+            upload_seeds(d, seeds, ctx->width, h2d);
         }
         for (DeviceState& d : ctx->dev) { CUDA_OK(cudaSetDevice(d.device)); CUDA_OK(cudaStreamSynchronize(d.stream)); }
+    });
+}
+
+// ---- frames: the fused gather ------------------------------------------------------------------------------------
+int ptc_frame_create(int device, int32_t width, int32_t height, int32_t format, ptc_frame** frame, char* err, int errlen) {
+    if (frame) *frame = nullptr;
+    return guarded(err, errlen, [&] {
+        if (!frame) fail("ptc_frame_create: NULL argument");
+        if (width <= 0 || height <= 0 || (long long)width * height > (1ll << 30)) fail("ptc_frame_create: bad size %dx%d", width, height);
+        if (format != PTC_FRAME_F64 && format != PTC_FRAME_F32) fail("ptc_frame_create: unknown format %d", format);
+        if (ptc_device_count() <= 0) fail("no usable CUDA device; libptcuda has no CPU fallback");
+        std::unique_ptr<ptc_frame> f(new ptc_frame);
+        f->device = device < 0 ? 0 : device; f->width = width; f->height = height; f->format = format; f->owner = true;
+        CUDA_OK(cudaSetDevice(f->device));
+        CUDA_OK(cudaMalloc(&f->data, f->bytes()));          // plain cudaMalloc: exportable through CUDA IPC, reachable by peer stores
+        CUDA_OK(cudaMemset(f->data, 0, f->bytes()));
+        *frame = f.release();
+    });
+}
+
+int ptc_frame_export(ptc_frame* frame, void* handle64, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!frame || !handle64) fail("ptc_frame_export: NULL argument");
+        if (!frame->owner) fail("ptc_frame_export: only the process that created a frame can export it");
+        static_assert(sizeof(cudaIpcMemHandle_t) == PTC_FRAME_HANDLE_BYTES, "handle size");
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaSetDevice(frame->device));
+        CUDA_OK(cudaIpcGetMemHandle(&h, frame->data));
+        std::memcpy(handle64, &h, sizeof h);
+    });
+}
+
+int ptc_frame_import(int device, const void* handle64, int32_t width, int32_t height, int32_t format, ptc_frame** frame, char* err, int errlen) {
+    if (frame) *frame = nullptr;
+    return guarded(err, errlen, [&] {
+        if (!frame || !handle64) fail("ptc_frame_import: NULL argument");
+        if (format != PTC_FRAME_F64 && format != PTC_FRAME_F32) fail("ptc_frame_import: unknown format %d", format);
+        std::unique_ptr<ptc_frame> f(new ptc_frame);
+        f->device = device < 0 ? 0 : device; f->width = width; f->height = height; f->format = format; f->owner = false;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, sizeof h);
+        CUDA_OK(cudaSetDevice(f->device));                  // the mapping is made for the importing process's current device
+        CUDA_OK(cudaIpcOpenMemHandle(&f->data, h, cudaIpcMemLazyEnablePeerAccess));
+        *frame = f.release();
+    });
+}
+
+int ptc_frame_read(ptc_frame* frame, void* out, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!frame || !out) fail("ptc_frame_read: NULL argument");
+        CUDA_OK(cudaSetDevice(frame->device));
+        CUDA_OK(cudaMemcpy(out, frame->data, frame->bytes(), cudaMemcpyDeviceToHost));
+    });
+}
+
+int ptc_frame_device_pointer(ptc_frame* frame, void** dev_ptr, int64_t* bytes, int32_t* cuda_device) {
+    if (!frame) return 1;
+    if (dev_ptr) *dev_ptr = frame->data;
+    if (bytes) *bytes = int64_t(frame->bytes());
+    if (cuda_device) *cuda_device = frame->device;
+    return 0;
+}
+
+void ptc_frame_destroy(ptc_frame* frame) {
+    if (!frame) return;
+    cudaSetDevice(frame->device);
+    if (frame->data) { if (frame->owner) cudaFree(frame->data); else cudaIpcCloseMemHandle(frame->data); }
+    cudaGetLastError();
+    delete frame;
+}
+
+int ptc_set_frame(ptc_context* ctx, ptc_frame* frame, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!ctx) fail("ptc_set_frame: NULL context");
+        if (frame) {
+            if (frame->width != ctx->width || frame->height != ctx->height)
+                fail("ptc_set_frame: frame is %dx%d, the context renders %dx%d", frame->width, frame->height, ctx->width, ctx->height);
+            for (DeviceState& d : ctx->dev) {
+                if (d.device == frame->device || !frame->owner) continue;     // an IPC mapping is already addressable from its device
+                int can = 0;
+                CUDA_OK(cudaDeviceCanAccessPeer(&can, d.device, frame->device));
+                if (!can) fail("ptc_set_frame: device %d cannot store into device %d's memory (no peer access)", d.device, frame->device);
+                CUDA_OK(cudaSetDevice(d.device));
+                cudaError_t pe = cudaDeviceEnablePeerAccess(frame->device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_OK(pe);
+                cudaGetLastError();
+            }
+        }
+        ctx->frame = frame;
     });
 }
 
 int ptc_device_framebuffer(ptc_context* ctx, int local_index, void** dev_ptr, int64_t* n_doubles, int32_t* cuda_device) {
     if (!ctx || local_index < 0 || local_index >= int(ctx->dev.size())) return 1;
     DeviceState& d = ctx->dev[size_t(local_index)];
-    if (dev_ptr) *dev_ptr = d.out;
-    if (n_doubles) *n_doubles = int64_t(d.rows.size()) * ctx->width * 4;
+    if (gathered(*ctx)) {       // every device stored into dev[0]'s buffer: device 0 exposes all the context's rows, the others nothing
+        if (dev_ptr) *dev_ptr = local_index == 0 ? ctx->gather : nullptr;
+        if (n_doubles) *n_doubles = local_index == 0 ? int64_t(ctx->rows.size()) * ctx->width * 4 : 0;
+    } else {
+        if (dev_ptr) *dev_ptr = d.out;
+        if (n_doubles) *n_doubles = int64_t(d.rows.size()) * ctx->width * 4;
+    }
     if (cuda_device) *cuda_device = d.device;
     return 0;
 }
@@ -1054,10 +1280,10 @@ int ptc_render(const ptc_job* job, double* out_rgba, char* err, int errlen) {
     return rc;
 }
 
-int ptc_render_flat(const void* objects, int32_t n_objects, const void* triangles, int32_t n_triangles, const void* groups,
-                    int32_t n_groups, const void* camera, const uint8_t* tex_plane, const uint8_t* tex_sphere,
-                    const uint8_t* tex_cube, const int32_t* tex_dims, const double* seeds, int32_t samples, int32_t precision,
-                    int32_t rng_mode, const int32_t* devices, int32_t n_devices, double* out_rgba, char* err, int errlen) {
+int ptc_render_flat2(const void* objects, int32_t n_objects, const void* triangles, int32_t n_triangles, const void* groups,
+                     int32_t n_groups, const void* camera, const uint8_t* tex_plane, const uint8_t* tex_sphere,
+                     const uint8_t* tex_cube, const int32_t* tex_dims, const double* seeds, int32_t samples, int32_t precision,
+                     int32_t rng_mode, int32_t features, const int32_t* devices, int32_t n_devices, double* out_rgba, char* err, int errlen) {
     ptc_job job;
     std::memset(&job, 0, sizeof job);
     job.abi_version = PTC_ABI_VERSION;
@@ -1070,9 +1296,17 @@ int ptc_render_flat(const void* objects, int32_t n_objects, const void* triangle
         job.tex[k] = tex[k];
         if (tex[k] && tex_dims) { job.tex_w[k] = tex_dims[3 * k]; job.tex_h[k] = tex_dims[3 * k + 1]; job.tex_layers[k] = tex_dims[3 * k + 2]; }
     }
-    job.seeds = seeds; job.samples = samples; job.precision = precision; job.rng_mode = rng_mode;
+    job.seeds = seeds; job.samples = samples; job.precision = precision; job.rng_mode = rng_mode; job.features = features;
     job.devices = devices; job.n_devices = devices ? n_devices : 0;
     return ptc_render(&job, out_rgba, err, errlen);
+}
+
+int ptc_render_flat(const void* objects, int32_t n_objects, const void* triangles, int32_t n_triangles, const void* groups,
+                    int32_t n_groups, const void* camera, const uint8_t* tex_plane, const uint8_t* tex_sphere,
+                    const uint8_t* tex_cube, const int32_t* tex_dims, const double* seeds, int32_t samples, int32_t precision,
+                    int32_t rng_mode, const int32_t* devices, int32_t n_devices, double* out_rgba, char* err, int errlen) {
+    return ptc_render_flat2(objects, n_objects, triangles, n_triangles, groups, n_groups, camera, tex_plane, tex_sphere, tex_cube, tex_dims, seeds,
+                            samples, precision, rng_mode, 0, devices, n_devices, out_rgba, err, errlen);
 }
 
 // Test hook (not part of the drop-in surface): evaluate noise3D on the device.
@@ -1111,6 +1345,35 @@ int ptc_debug_fma_peak(int device, double* tflops, char* err, int errlen) {
         for (int rep = 0; rep < 6; ++rep) {                       // first launch = warm-up
             CUDA_OK(cudaEventRecord(e0));
             ptk::fma_peak_kernel<<<blocks, threads>>>(out, iters);
+            CUDA_OK(cudaEventRecord(e1));
+            CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+        CUDA_OK(cudaGetLastError());
+        *tflops = 2.0 * 8 * 16 * double(iters) * blocks * threads / (best * 1e-3) / 1e12;
+    });
+}
+
+// The FP64 twin: achieved DFMA throughput in TFLOP/s (the roofline of the fp64 mode).
+int ptc_debug_dfma_peak(int device, double* tflops, char* err, int errlen) {
+    return guarded(err, errlen, [&] {
+        if (!tflops) fail("ptc_debug_dfma_peak: tflops is NULL");
+        if (ptc_device_count() <= 0) fail("no usable CUDA device; libptcuda has no CPU fallback");
+        CUDA_OK(cudaSetDevice(device));
+        int sms = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const int blocks = sms * 8, threads = 256, iters = 1024;
+        double* out = nullptr;
+        CUDA_OK(cudaMalloc(&out, size_t(blocks) * threads * sizeof(double)));
+        cudaEvent_t e0, e1;
+        CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; ++rep) {                       // first launch = warm-up
+            CUDA_OK(cudaEventRecord(e0));
+            ptk::dfma_peak_kernel<<<blocks, threads>>>(out, iters);
             CUDA_OK(cudaEventRecord(e1));
             CUDA_OK(cudaEventSynchronize(e1));
             float ms = 0.f;

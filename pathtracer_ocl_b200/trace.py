@@ -21,6 +21,9 @@ _LIB_PATH = os.environ.get("PTCUDA_LIB") or os.path.join(_HERE, "libptcuda.so") 
 PTC_ABI_VERSION = 1
 FP32, FP64 = 0, 1
 RNG_PARITY, RNG_FAST = 0, 1
+FEATURE_NEE, FEATURE_CYLINDER_CAPS = 1, 2          # code paths the reference ships disabled (ptcuda.h)
+FRAME_F64, FRAME_F32 = 0, 1
+FRAME_HANDLE_BYTES = 64
 
 
 class PtcJob(C.Structure):
@@ -35,7 +38,7 @@ class PtcJob(C.Structure):
         ("samples", C.c_int32), ("precision", C.c_int32), ("rng_mode", C.c_int32),
         ("devices", C.POINTER(C.c_int32)), ("n_devices", C.c_int32),
         ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("rows_per_tile", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("features", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -51,8 +54,9 @@ class PtcStats(C.Structure):
 
 
 EXPORTS = ["ptc_device_count", "ptc_device_name", "ptc_render", "ptc_open", "ptc_trace", "ptc_read", "ptc_get_stats",
-           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_plan_rows", "ptc_version", "ptc_render_flat", "ptc_trim",
-           "ptc_trace_range", "ptc_reset", "ptc_read_rgba8"]
+           "ptc_close", "ptc_set_seeds", "ptc_device_framebuffer", "ptc_shard_rows", "ptc_plan_rows", "ptc_version", "ptc_render_flat", "ptc_render_flat2", "ptc_trim",
+           "ptc_trace_range", "ptc_reset", "ptc_read_rgba8", "ptc_read_f32", "ptc_frame_create", "ptc_frame_export",
+           "ptc_frame_import", "ptc_set_frame", "ptc_frame_read", "ptc_frame_device_pointer", "ptc_frame_destroy"]
 
 _lib = None
 
@@ -82,6 +86,15 @@ def lib() -> C.CDLL:
         L.ptc_trace_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int]
         L.ptc_reset.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.ptc_read_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_read_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_frame_create.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        L.ptc_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_frame_import.argtypes = [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        L.ptc_set_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ptc_frame_device_pointer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        L.ptc_frame_destroy.argtypes = [C.c_void_p]
+        L.ptc_debug_dfma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int]
         L.ptc_debug_mesh_index.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_char_p, C.c_int]
         L.ptc_debug_mesh_index.restype = C.c_int64
         L.ptc_debug_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int]
@@ -142,7 +155,7 @@ class _Job:
     """Keeps the numpy buffers alive next to the ctypes struct that points into them."""
 
     def __init__(self, objects, triangles, groups, camera, textures, sphere_textures, cube_textures, seeds, samples,
-                 precision, rng_mode, devices, shard_index, shard_count, rows_per_tile):
+                 precision, rng_mode, devices, shard_index, shard_count, rows_per_tile, features=0):
         self.objects = _as_bytes(objects, 1024, "objects")
         self.triangles = _as_bytes(triangles, 512, "triangles") if triangles is not None else np.zeros(0, np.uint8)
         self.groups = _as_bytes(groups, 256, "groups") if groups is not None else np.zeros(0, np.uint8)
@@ -171,6 +184,7 @@ class _Job:
             self._dev = (C.c_int32 * len(devices))(*devices)
             j.devices, j.n_devices = self._dev, len(devices)
         j.shard_index, j.shard_count, j.rows_per_tile = int(shard_index), int(shard_count), int(rows_per_tile)
+        j.features = int(features)
         self.struct = j
 
 
@@ -180,9 +194,10 @@ class Context:
     def __init__(self, objects, triangles, groups, camera, textures=None, sphere_textures=None, cube_textures=None, *,
                  seeds, samples: int = 1, precision: int = FP32, rng_mode: int = RNG_PARITY,
                  devices: Optional[Sequence[int]] = None, shard_index: int = 0, shard_count: int = 1,
-                 rows_per_tile: int = 0):
+                 rows_per_tile: int = 0, features: int = 0):
         self._job = _Job(objects, triangles, groups, camera, textures, sphere_textures, cube_textures, seeds, samples,
-                         precision, rng_mode, list(devices) if devices else None, shard_index, shard_count, rows_per_tile)
+                         precision, rng_mode, list(devices) if devices else None, shard_index, shard_count, rows_per_tile,
+                         features)
         self.width, self.height = self._job.width, self._job.height
         self._h = C.c_void_p()
         err = C.create_string_buffer(512)
@@ -241,6 +256,21 @@ class Context:
             raise PtcError(err.value.decode())
         return out
 
+    def read_f32(self) -> np.ndarray:
+        """The frame as float32 RGBA (converted on the device; half of read()'s bytes)."""
+        out = np.empty((len(self.rows), self.width, 4), dtype=np.float32)
+        err = C.create_string_buffer(512)
+        if lib().ptc_read_f32(self._h, out.ctypes.data, err, 512) != 0:
+            raise PtcError(err.value.decode())
+        return out
+
+    def set_frame(self, frame: "Optional[Frame]") -> None:
+        """Attach a Frame: trace() then stores every pixel straight into it (by frame row); None detaches."""
+        err = C.create_string_buffer(512)
+        if lib().ptc_set_frame(self._h, frame._h if frame is not None else None, err, 512) != 0:
+            raise PtcError(err.value.decode())
+        self._frame = frame
+
     def set_seeds_ptr(self, ptr: int) -> None:
         err = C.create_string_buffer(512)
         if lib().ptc_set_seeds(self._h, C.c_void_p(ptr), err, 512) != 0:
@@ -276,9 +306,65 @@ class Context:
             pass
 
 
+class Frame:
+    """A whole-frame buffer on one device that sharded contexts render into directly (ptc_frame_*): the gather of
+    SURVEY.md 8e fused into the trace kernel's epilogue as peer stores.  `Frame(device, w, h)` allocates;
+    `export()` gives the 64-byte handle another process turns into its own mapping with `Frame.attach(...)`."""
+
+    def __init__(self, device: int, width: int, height: int, fmt: int = FRAME_F64, _handle: Optional[bytes] = None):
+        self.width, self.height, self.format, self.device = width, height, fmt, device
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        if _handle is None:
+            rc = lib().ptc_frame_create(device, width, height, fmt, C.byref(self._h), err, 512)
+        else:
+            buf = C.create_string_buffer(_handle, FRAME_HANDLE_BYTES)
+            rc = lib().ptc_frame_import(device, buf, width, height, fmt, C.byref(self._h), err, 512)
+        if rc != 0:
+            raise PtcError(err.value.decode())
+
+    @classmethod
+    def attach(cls, device: int, handle: bytes, width: int, height: int, fmt: int = FRAME_F64) -> "Frame":
+        return cls(device, width, height, fmt, _handle=handle)
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(FRAME_HANDLE_BYTES)
+        err = C.create_string_buffer(512)
+        if lib().ptc_frame_export(self._h, buf, err, 512) != 0:
+            raise PtcError(err.value.decode())
+        return buf.raw
+
+    def read(self, out_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        """[H, W, 4] float64 (float32 for FRAME_F32); with out_ptr the bytes go to that host address instead."""
+        out = None
+        if out_ptr is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.float32 if self.format == FRAME_F32 else np.float64)
+            out_ptr = out.ctypes.data
+        err = C.create_string_buffer(512)
+        if lib().ptc_frame_read(self._h, C.c_void_p(out_ptr), err, 512) != 0:
+            raise PtcError(err.value.decode())
+        return out
+
+    def device_pointer(self):
+        p, n, d = C.c_void_p(), C.c_int64(), C.c_int32()
+        lib().ptc_frame_device_pointer(self._h, C.byref(p), C.byref(n), C.byref(d))
+        return p.value, n.value, d.value
+
+    def close(self) -> None:
+        if self._h:
+            lib().ptc_frame_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def Trace(objects, triangles, groups, device_index: int, samples: int, camera, textures=None, sphere_textures=None,
           cube_textures=None, *, seeds: Optional[np.ndarray] = None, precision: int = FP32, rng_mode: int = RNG_PARITY,
-          devices: Optional[Sequence[int]] = None) -> np.ndarray:
+          devices: Optional[Sequence[int]] = None, features: int = 0) -> np.ndarray:
     """Drop-in for ``ocl.Trace`` (ocltracer.go:100).  Positional arguments as in the reference.
 
     ``seeds``: one float64 in [0,1) per pixel; when omitted they are drawn like the reference does
@@ -289,7 +375,7 @@ def Trace(objects, triangles, groups, device_index: int, samples: int, camera, t
     if seeds is None:
         seeds = np.random.random_sample(w * h)
     job = _Job(objects, triangles, groups, cam, textures, sphere_textures, cube_textures, seeds, samples, precision,
-               rng_mode, list(devices) if devices else [int(device_index)], 0, 1, 0)
+               rng_mode, list(devices) if devices else [int(device_index)], 0, 1, 0, features)
     out = np.empty(w * h * 4, dtype=np.float64)
     err = C.create_string_buffer(512)
     if lib().ptc_render(C.byref(job.struct), out.ctypes.data, err, 512) != 0:
@@ -325,6 +411,15 @@ def debug_fma_peak(device: int = 0) -> float:
     out = C.c_double(0.0)
     err = C.create_string_buffer(512)
     if lib().ptc_debug_fma_peak(int(device), C.byref(out), err, 512) != 0:
+        raise PtcError(err.value.decode())
+    return float(out.value)
+
+
+def debug_dfma_peak(device: int = 0) -> float:
+    """Measurement hook: achieved FP64 DFMA throughput of `device` in TFLOP/s (the fp64 mode's roofline)."""
+    out = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    if lib().ptc_debug_dfma_peak(int(device), C.byref(out), err, 512) != 0:
         raise PtcError(err.value.decode())
     return float(out.value)
 
