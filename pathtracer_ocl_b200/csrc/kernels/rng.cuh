@@ -16,10 +16,22 @@ namespace ptk {
 
 enum { RNG_PARITY = 0, RNG_FAST = 1 };
 
+// Constants of the canonical sine (oracle/canon_rng.h), in constant memory: a DFMA takes a 64-bit constant-bank
+// operand directly, whereas a literal has to be built in a uniform register pair first (two UMOVs per coefficient,
+// ~24 issue slots per pair of noise3D calls in round 1's SASS).
+__constant__ double c_sin[16] = {
+    0x1.45f306dc9c883p-2,      // 0: 1/pi
+    0x1.921fb54442d18p+1,      // 1: pi, high part
+    0x1.1a62633145c07p-53,     // 2: pi, low part
+    0x1.71b8ef6dcf572p-66, -0x1.2f49b46814157p-57, 0x1.952c77030ad4ap-49, -0x1.ae7f3e733b81fp-41, 0x1.6124613a86d09p-33,
+    -0x1.ae64567f544e4p-26, 0x1.71de3a556c734p-19, -0x1.a01a01a01a01ap-13, 0x1.1111111111111p-7, -0x1.5555555555555p-3,
+    6755399441055744.0,        // 13: 1.5 * 2^52
+    0.0, 0.0};
+
 __device__ __forceinline__ float sin_parity(float x) {
-    const double INV_PI = 0x1.45f306dc9c883p-2;
-    const double PI_HI = 0x1.921fb54442d18p+1;
-    const double PI_LO = 0x1.1a62633145c07p-53;
+    const double INV_PI = c_sin[0];
+    const double PI_HI = c_sin[1];
+    const double PI_LO = c_sin[2];
     double xd = (double)x;
     // q = rint(x/pi) by the add-and-subtract-1.5*2^52 trick (exact for |x/pi| < 2^51, ties to even like
     // rint); the parity of q is the low mantissa bit of the biased sum.  Avoids two 64-bit conversions.
@@ -30,25 +42,25 @@ __device__ __forceinline__ float sin_parity(float x) {
     double r = __fma_rn(-q, PI_HI, xd);
     r = __fma_rn(-q, PI_LO, r);
     double r2 = __dmul_rn(r, r);
-    double p = 0x1.71b8ef6dcf572p-66;
-    p = __fma_rn(p, r2, -0x1.2f49b46814157p-57);
-    p = __fma_rn(p, r2, 0x1.952c77030ad4ap-49);
-    p = __fma_rn(p, r2, -0x1.ae7f3e733b81fp-41);
-    p = __fma_rn(p, r2, 0x1.6124613a86d09p-33);
-    p = __fma_rn(p, r2, -0x1.ae64567f544e4p-26);
-    p = __fma_rn(p, r2, 0x1.71de3a556c734p-19);
-    p = __fma_rn(p, r2, -0x1.a01a01a01a01ap-13);
-    p = __fma_rn(p, r2, 0x1.1111111111111p-7);
-    p = __fma_rn(p, r2, -0x1.5555555555555p-3);
+    double p = c_sin[3];
+    p = __fma_rn(p, r2, c_sin[4]);
+    p = __fma_rn(p, r2, c_sin[5]);
+    p = __fma_rn(p, r2, c_sin[6]);
+    p = __fma_rn(p, r2, c_sin[7]);
+    p = __fma_rn(p, r2, c_sin[8]);
+    p = __fma_rn(p, r2, c_sin[9]);
+    p = __fma_rn(p, r2, c_sin[10]);
+    p = __fma_rn(p, r2, c_sin[11]);
+    p = __fma_rn(p, r2, c_sin[12]);
     double s = __fma_rn(__dmul_rn(r, r2), p, r);
     if (qi & 1) s = -s;
     return __double2float_rn(s);
 }
 
 __device__ __forceinline__ float sin_fast(float x) {
-    const double INV_PI = 0x1.45f306dc9c883p-2;
-    const double PI_HI = 0x1.921fb54442d18p+1;
-    const double PI_LO = 0x1.1a62633145c07p-53;
+    const double INV_PI = c_sin[0];
+    const double PI_HI = c_sin[1];
+    const double PI_LO = c_sin[2];
     double xd = (double)x;
     const double MAGIC = 6755399441055744.0;
     double biased = __dadd_rn(__dmul_rn(xd, INV_PI), MAGIC);

@@ -32,7 +32,6 @@
 //     The fp32 instantiation uses the SFU approximations (rcp / rsqrt / sqrt / sin / cos) for its
 //     own arithmetic; the RNG and the texture filter stay exactly rounded in both modes.
 #pragma once
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -67,7 +66,7 @@ namespace ptk {
 constexpr int kMaxObjects = 16;
 // Unrolled slots of the intersection loop (see Params::fast): three runs in scene order -- spheres, planes, spheres --
 // which is how Cornell-box scenes are laid out (light first, walls, then the contents).
-constexpr int kFastA = 4, kFastB = 8, kFastC = 6, kFastSlots = kFastA + kFastB + kFastC;
+constexpr int kFastA = 2, kFastB = 8, kFastC = 6, kFastSlots = kFastA + kFastB + kFastC;
 constexpr int kBlockThreads = PTK_BLOCK_THREADS;
 constexpr int kBlockWarps = kBlockThreads / 32;
 constexpr int kMaxCluster = 8;             // CTAs per cluster (portable limit): up to kMaxCluster * kBlockWarps sample slices per pixel
@@ -157,7 +156,10 @@ template <typename R> struct alignas(16) DObjShade {
 //   plane:  (a, b, c, d) = row 1 of `inverse`: object-space y of a point is a*x + b*y + c*z + d (tracer.cl:478-483)
 //   sphere: (cx, cy, cz, r^2): the world-space sphere |p - c|^2 = r^2 that the unit sphere maps to when `inverse` is a
 //           similarity (scale s = 1/r): t solves |ro + t*rd - c|^2 = r^2, the reference's quadratic (tracer.cl:448-476)
-//           divided through by s^2.
+//           divided through by s^2;
+//           fast_kind 1, axis-aligned ellipsoid (`inverse` = diag(sx, sy, sz) * translate(-c), e.g. the flattened
+//           ceiling light of the Cornell scenes): (cx, cy, cz, -) plus fast2 = (sx, sy, sz, -): the quadratic of
+//           |S (ro + t*rd - c)|^2 = 1.
 // Slots form three runs -- kFastA spheres, kFastB planes, kFastC spheres -- filled by the host with the longest
 // subsequence of the scene's objects that fits "spheres, planes, spheres" in scene order; each run stops at its count.
 // Fast objects therefore meet in scene order and ties resolve as upstream (first recorded wins, tracer.cl:731-739);
@@ -186,6 +188,8 @@ constexpr int kEmptyChild = (int)0x80000000;
 
 template <typename R> struct Params {
     DFast<R> fast[kFastSlots];  // runs A (spheres) | B (planes) | C (spheres)
+    DFast<R> fast2[kFastSlots]; // sphere slots of kind 1: the diagonal of `inverse`
+    int fast_kind[kFastSlots];  // sphere slots: 0 = similarity, 1 = axis-aligned ellipsoid
     int fast_n[4];              // objects in run A, B, C
     int fast_obj[kFastSlots];   // slot -> object index
     DObjHot<R> hot[kMaxObjects];    // read by the slow loop and the mesh walk only
@@ -631,8 +635,15 @@ __device__ __forceinline__ void fast_plane(const Params<R>& P, V3<R> ro, V3<R> r
 template <typename R, int SLOT>
 __device__ __forceinline__ void fast_sphere(const Params<R>& P, V3<R> ro, V3<R> rd, R a, R inv_a, R eps, Hit<R>& h) {
     const DFast<R>& f = P.fast[SLOT];                            // tracer.cl:448-476: both roots recorded when disc > 0
-    const V3<R> oc = {ro.x - f.a, ro.y - f.b, ro.z - f.c};
-    const R hb = dot(rd, oc), c = dot(oc, oc) - f.d;
+    V3<R> oc = {ro.x - f.a, ro.y - f.b, ro.z - f.c}, dd = rd;
+    R c1 = f.d;
+    if (P.fast_kind[SLOT] != 0) {                                // ellipsoid: scale the offset and the direction, own a and 1/a
+        const DFast<R>& g = P.fast2[SLOT];
+        oc = {oc.x * g.a, oc.y * g.b, oc.z * g.c};
+        dd = {rd.x * g.a, rd.y * g.b, rd.z * g.c};
+        a = dot(dd, dd); inv_a = m_rcp(a); c1 = R(1);
+    }
+    const R hb = dot(dd, oc), c = dot(oc, oc) - c1;
     const R sq = sqrt_pos(hb * hb - a * c);
     const R t0 = (-hb - sq) * inv_a, t1 = (-hb + sq) * inv_a;    // t0 <= t1: the first root beyond EPSILON is the pair's winner
     const R t = t0 > eps ? t0 : t1;
@@ -878,6 +889,21 @@ __device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, P
     return (ob.emission[0] > R(0)) || !(s.b < 10u && s.effective < 4u);        // tracer.cl:1107, 884
 }
 
+// Thread-block cluster primitives, spelled in PTX on 32-bit shared-window addresses: going through cooperative_groups'
+// generic pointers made the compiler address EVERY shared array of the kernel through the cluster window (an S2UR
+// SR_CgaCtaId + LEA per access group in the hot loop).
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_map_shared(unsigned addr, unsigned rank) {
+    unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ double cluster_ld_f64(unsigned addr) {
+    double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory"); return v;
+}
+
 // Frame geometry of a thread.  A warp covers an 8x4 pixel tile for one sample slice.  The warps of a block are
 // slices_per_block slices of kBlockWarps / slices_per_block consecutive tiles; the blocks of a cluster hold the
 // remaining slices of the same tiles (slice = cluster rank * slices_per_block + slice within the block).
@@ -904,9 +930,7 @@ template <typename R> __device__ __forceinline__ PixelSlot pixel_slot(const Para
 template <typename R, int RNG, bool GROUPS>
 __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS_F64) : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
     extern __shared__ int2 mesh_stacks[];       // GROUPS: one stack of P.stack_entries per 8-lane group (sized by the host from the scene's BVH)
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned cluster_size = cluster.num_blocks(), cluster_rank = cluster.block_rank();
+    const unsigned cluster_size = cluster_nctarank(), cluster_rank = cluster_ctarank();
     const PixelSlot px = pixel_slot(P, cluster_rank, cluster_size);
     const int lane = threadIdx.x & 31;
     const int W = P.cam.width;
@@ -981,18 +1005,19 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
     // cluster through distributed shared memory -- and are summed in slice order (deterministic: the same order for
     // any grid shape), so no per-slice partial sums ever go to HBM.  The first slice's thread of the cluster's first
     // block owns the pixel's store; with out_frame_rows that store goes straight into the (possibly remote) frame.
-    if (cluster_size > 1) cluster.sync(); else __syncthreads();
+    if (cluster_size > 1) cluster_sync(); else __syncthreads();
     const int spb = P.slices_per_block;
     const int w = threadIdx.x >> 5;
     if (cluster_rank == 0 && (w % spb) == 0 && px.has_pixel) {
         double r = 0.0, g = 0.0, b = 0.0;
         const size_t lpix = (size_t)px.ly * W + px.lx;
         if (P.acc) { const double4 a = P.acc[lpix]; r = a.x; g = a.y; b = a.z; }
+        const unsigned sums = (unsigned)__cvta_generic_to_shared(&col_sum[0][0]);
         for (unsigned cr = 0; cr < cluster_size; ++cr) {
-            const double* remote = cluster_size > 1 ? cluster.map_shared_rank(&col_sum[0][0], cr) : &col_sum[0][0];
+            const unsigned remote = cluster_map_shared(sums, cr);       // block cr's col_sum (this block's own for cr == rank)
             for (int q = 0; q < spb; ++q) {
-                const int t = threadIdx.x + 32 * q;
-                r += remote[t]; g += remote[kBlockThreads + t]; b += remote[2 * kBlockThreads + t];
+                const unsigned t = (threadIdx.x + 32 * q) * 8u;
+                r += cluster_ld_f64(remote + t); g += cluster_ld_f64(remote + kBlockThreads * 8u + t); b += cluster_ld_f64(remote + 2u * kBlockThreads * 8u + t);
             }
         }
         if (P.acc) P.acc[lpix] = make_double4(r, g, b, 0.0);
@@ -1001,7 +1026,7 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
         if (P.out_f32) reinterpret_cast<float4*>(P.out)[opix] = make_float4((float)(r * wgt), (float)(g * wgt), (float)(b * wgt), 1.0f);
         else reinterpret_cast<double4*>(P.out)[opix] = make_double4(r * wgt, g * wgt, b * wgt, 1.0);
     }
-    if (cluster_size > 1) cluster.sync();          // remote shared memory stays alive until the first block has read it
+    if (cluster_size > 1) cluster_sync();          // remote shared memory stays alive until the first block has read it
 }
 
 // RGBA double -> float (the reference's frontend keeps float64 but its .raw writer and canvas store float32-range data,

@@ -58,7 +58,8 @@ void set_err(char* err, int errlen, const char* msg) {
 template <typename R> struct HostScene {
     ptk::DObjHot<R> hot[ptk::kMaxObjects];
     ptk::DFast<R> fast[ptk::kFastSlots];
-    int fast_n[4], fast_obj[ptk::kFastSlots];
+    ptk::DFast<R> fast2[ptk::kFastSlots];
+    int fast_n[4], fast_obj[ptk::kFastSlots], fast_kind[ptk::kFastSlots];
     int slow_obj[ptk::kMaxObjects], n_slow = 0;
     int mesh_obj[ptk::kMaxObjects], n_mesh = 0;
     int stack_need = 0;        // deepest deferred-child stack any mesh of the scene can need
@@ -447,7 +448,10 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
     // relative order; other analytic objects take the slow loop; groups with triangles the mesh walk.
     out.n_slow = out.n_mesh = 0;
     for (int k = 0; k < 4; ++k) out.fast_n[k] = 0;
-    for (int k = 0; k < ptk::kFastSlots; ++k) { out.fast_obj[k] = -1; out.fast[k] = ptk::DFast<R>{R(0), R(0), R(0), R(0)}; }
+    for (int k = 0; k < ptk::kFastSlots; ++k) {
+        out.fast_obj[k] = -1; out.fast_kind[k] = 0;
+        out.fast[k] = out.fast2[k] = ptk::DFast<R>{R(0), R(0), R(0), R(0)};
+    }
     const int run_begin[3] = {0, ptk::kFastA, ptk::kFastA + ptk::kFastB}, run_cap[3] = {ptk::kFastA, ptk::kFastB, ptk::kFastC};
     int run = 0;                                                     // run currently being filled (never goes back)
     for (int i = 0; i < job.n_objects; ++i) {
@@ -455,8 +459,8 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
         const int type = out.hot[i].type;
         if (type == 4) { if (out.mesh[size_t(i)].bvh_root >= 0) out.mesh_obj[out.n_mesh++] = i; continue; }
         if (type < 0 || type > 3) continue;                          // unknown type: never hit (tracer.cl:549-597 has no branch for it)
-        ptk::DFast<R> rec{R(0), R(0), R(0), R(0)};
-        int want = -1;                                               // 0: a sphere run, 1: the plane run
+        ptk::DFast<R> rec{R(0), R(0), R(0), R(0)}, rec2{R(0), R(0), R(0), R(0)};
+        int want = -1, kind = 0;                                     // 0: a sphere run, 1: the plane run
         if (type == 0) {
             rec = ptk::DFast<R>{R(s.inverse[4]), R(s.inverse[5]), R(s.inverse[6]), R(s.inverse[7])};
             want = 1;
@@ -474,6 +478,12 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
                              cz = -(m[2] * m[3] + m[6] * m[7] + m[10] * m[11]) / s2;
                 rec = ptk::DFast<R>{R(cx), R(cy), R(cz), R(1.0 / s2)};
                 want = 0;
+            } else if (m[1] == 0.0 && m[2] == 0.0 && m[4] == 0.0 && m[6] == 0.0 && m[8] == 0.0 && m[9] == 0.0 && m[0] != 0.0 && m[5] != 0.0 &&
+                       m[10] != 0.0 && std::isfinite(m[0] * m[5] * m[10]) && m[12] == 0.0 && m[13] == 0.0 && m[14] == 0.0 && m[15] == 1.0) {
+                // axis-aligned ellipsoid: inverse = diag(sx, sy, sz) p + t = S (p - c) with c = -t / s
+                rec = ptk::DFast<R>{R(-m[3] / m[0]), R(-m[7] / m[5]), R(-m[11] / m[10]), R(1)};
+                rec2 = ptk::DFast<R>{R(m[0]), R(m[5]), R(m[10]), R(0)};
+                want = 0; kind = 1;
             }
         }
         int slot = -1;
@@ -482,7 +492,7 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
             if (run == 0 && out.fast_n[0] < run_cap[0]) slot = run_begin[0] + out.fast_n[0]++;
             else if (out.fast_n[2] < run_cap[2]) { run = 2; slot = run_begin[2] + out.fast_n[2]++; }
         }
-        if (slot >= 0) { out.fast[slot] = rec; out.fast_obj[slot] = i; }
+        if (slot >= 0) { out.fast[slot] = rec; out.fast2[slot] = rec2; out.fast_kind[slot] = kind; out.fast_obj[slot] = i; }
         else out.slow_obj[out.n_slow++] = i;
     }
     const auto* cam = static_cast<const ptw_camera*>(job.camera);
@@ -658,6 +668,8 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     std::memcpy(P.hot, s.hot, sizeof P.hot);
     std::memcpy(P.fast, s.fast, sizeof P.fast);
     std::memcpy(P.fast_n, s.fast_n, sizeof P.fast_n);
+    std::memcpy(P.fast2, s.fast2, sizeof P.fast2);
+    std::memcpy(P.fast_kind, s.fast_kind, sizeof P.fast_kind);
     std::memcpy(P.fast_obj, s.fast_obj, sizeof P.fast_obj);
     std::memcpy(P.slow_obj, s.slow_obj, sizeof P.slow_obj);
     std::memcpy(P.mesh_obj, s.mesh_obj, sizeof P.mesh_obj);
@@ -785,10 +797,11 @@ void destroy(ptc_context* c) {
 // per pixel, and blocks that live for the whole frame leave a long tail (measured on B200: a 1/8-frame shard ran
 // 36.3 ms with 1 slice, 29.3 ms with 32), so each pixel's samples are split into interleaved slices until there are
 // ~16x the resident thread capacity in total threads; scenes with meshes, whose pixels differ several-fold in cost,
-// get 8x finer slices (teapot 2.83 -> 3.12 Gpaths/s from 4 to 32 slices).  A power of two, at most
+// get 2x finer slices (round 2, whole frame on one B200, teapot / gopher Gpaths/s at 1, 2, 4, 8, 16, 32 slices:
+// 2.30 / 1.75, 3.12 / 2.22, 3.54 / 2.58, 3.67 / 2.62, 3.50 / 2.49, 3.44 / 2.45).  A power of two, at most
 // kBlockWarps * kMaxCluster = 32: all slices of a pixel sit in one thread-block cluster, which reduces them.
 int plan_slices(long long px, int sm_count, bool meshes, int samples) {
-    const long long want = (long long)sm_count * 2048 * (meshes ? 128 : 16);
+    const long long want = (long long)sm_count * 2048 * (meshes ? 32 : 16);
     long long sl = px ? (want + px - 1) / px : 1;
     if (const char* ov = std::getenv("PTC_SLICES")) sl = std::atoll(ov);    // tuning override
     const long long cap = std::min<long long>(samples, ptk::kBlockWarps * ptk::kMaxCluster);
