@@ -464,13 +464,37 @@ __device__ __forceinline__ int group_min(int v) {
     v = min(v, __shfl_xor_sync(kFullMask, v, 1)); v = min(v, __shfl_xor_sync(kFullMask, v, 2)); return min(v, __shfl_xor_sync(kFullMask, v, 4));
 }
 
+__device__ __forceinline__ unsigned group_min(unsigned v) {
+    v = min(v, __shfl_xor_sync(kFullMask, v, 1)); v = min(v, __shfl_xor_sync(kFullMask, v, 2)); return min(v, __shfl_xor_sync(kFullMask, v, 4));
+}
+// The per-group traversal stacks live in dynamic shared memory and are addressed by their 32-bit shared-window
+// address, computed once per thread (through a generic pointer the compiler re-derived the window base -- S2UR
+// SR_CgaCtaId, MOV, LEA -- at every push and pop).
+__device__ __forceinline__ void stack_store(unsigned addr, int code, int key) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(addr), "r"(code), "r"(key) : "memory");
+}
+__device__ __forceinline__ int2 stack_load(unsigned addr) {
+    int2 e; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr) : "memory"); return e;
+}
+
 // One mesh object against the rays of the lanes with `want` set.  Called by all 32 lanes.  `ro`, `rd`:
-// this lane's ray in world space.  `stk`: this lane's GROUP's stack in shared memory.
+// this lane's ray in world space.  `stk`: shared-window address of this lane's GROUP's stack.
+//
+// A step of the walk, per group: every lane does its share (inner node: lane c tests child c's box; leaf: lane c
+// tests triangle c and, if it is a candidate, checks at once that the reference would have tested it), then
+//   * the nearest hit child comes out of ONE unsigned min over packed keys -- the entry distance's float bits with
+//     the lane number in the three low bits -- so the minimum names its lane (no second ballot, no find-first-set);
+//     the other hit children are pushed with their key as the distance bound;
+//   * accepted triangle candidates are reduced separately, in the kernel's arithmetic type and only on the (rare)
+//     steps that have one: smallest t, then lowest rank (= the reference's recording order) with the lane packed
+//     into the rank key.
 template <typename R>
-__device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& ob, const DMesh<R>& m, int j, V3<R> ro, V3<R> rd, bool want, int lane, Hit<R>& h, int2* __restrict__ stk) {
+__device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& ob, const DMesh<R>& m, int j, V3<R> ro, V3<R> rd, bool want, int lane, Hit<R>& h, unsigned stk) {
     const R eps = P.eps;
     const int sub = lane & 7, gbase = lane & 24, grp = lane >> 3;
+    const unsigned below = (1u << sub) - 1u;
     constexpr int kDone = 0x7fffffff;
+    constexpr unsigned kNoKey = 0xffffffffu;
     unsigned todo = __ballot_sync(kFullMask, want);
     while (todo) {                                                    // a round: up to four rays, one per group
         // owners of this round: the four lowest set bits of `todo`
@@ -494,21 +518,18 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& o
         int cur = active ? m.bvh_root : kDone, sp = 0;
 
         while (__any_sync(kFullMask, cur != kDone)) {
-            const bool inner = cur >= 0 && cur != kDone;
-            const bool leaf = cur < 0;
-            const R limit = ct * R(1.0001);
-            // per-lane work: one child box (inner) or one triangle (leaf)
-            R key = m_huge<R>();
-            bool flag = false;
-            int code = 0, rank = 0, ref = 0, slot = 0;
-            R tu = R(0), tv = R(0);
-            if (inner) {
+            unsigned key = kNoKey;                                    // inner: packed entry distance of this lane's child
+            int code = 0;
+            bool cand = false;                                        // leaf: this lane's triangle is an accepted candidate
+            int rank = 0, slot = 0;
+            R tt = R(0), tu = R(0), tv = R(0);
+            if (cur >= 0 && cur != kDone) {                           // inner node: one child box per lane
                 const V4<R> a = ldg4(&P.wide[(cur * kWide + sub) * 2]), b = ldg4(&P.wide[(cur * kWide + sub) * 2 + 1]);
                 code = child_code(a.w);
                 R tn;
-                flag = keep_box(o, k, a.x, b.x, a.y, b.y, a.z, b.z, limit, tn) && code != kEmptyChild;
-                if (flag) key = tn;
-            } else if (leaf) {
+                if (keep_box(o, k, a.x, b.x, a.y, b.y, a.z, b.z, ct * R(1.0001), tn) && code != kEmptyChild)
+                    key = ((unsigned)stack_key(tn) & 0x7ffffff8u) | (unsigned)sub;
+            } else if (cur < 0) {                                     // leaf: one triangle per lane
                 const int lc = ~cur, count = lc & 15;
                 slot = (lc >> 4) + sub;
                 if (sub < count) {                                    // Moeller-Trumbore, tracer.cl:640-675
@@ -525,56 +546,40 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& o
                     const R t = f * dot(e2, sxe1);
                     const bool ok = !(m_abs(det) < eps) && !(u < R(0) || u > R(1)) && !(v < R(0) || (u + v) > R(1));
                     if (ok && t > eps && t <= ct) {
-                        const int2 info = __ldg(&P.tri_info[slot]);
-                        rank = info.x; ref = info.y;
-                        flag = t < ct || rank < crank;
-                        if (flag) { key = t; tu = u; tv = v; }
+                        const int2 info = __ldg(&P.tri_info[slot]);   // (rank in the reference's recording order, reference node)
+                        if ((t < ct || info.x < crank) && reference_tests_node(P, o, d, s, info.y, whole_chain)) {
+                            cand = true; rank = info.x; tt = t; tu = u; tv = v;
+                        }
                     }
                 }
             }
-            // nearest hit child / closest candidate of each group
-            R kmin = group_min(key);
-            unsigned sel_bits = (__ballot_sync(kFullMask, flag && key == kmin) >> gbase) & 0xffu;
-            const unsigned hit_bits = (__ballot_sync(kFullMask, flag) >> gbase) & 0xffu;
-            int sel = sel_bits ? __ffs(sel_bits) - 1 : 0;
+            // nearest hit child of each group; the others go to the stack
+            const unsigned kmin = group_min(key);
+            const unsigned hit_bits = (__ballot_sync(kFullMask, key != kNoKey) >> gbase) & 0xffu;
+            const int sel = (int)(kmin & 7u);
             const int next_code = __shfl_sync(kFullMask, code, gbase + sel);
             int next = kDone;                                          // kDone here = "pop"
-            if (inner && hit_bits) {
+            if (kmin != kNoKey) {
                 next = next_code;
                 const unsigned others = hit_bits & ~(1u << sel);
-                if (flag && sub != sel) stk[sp + __popc(others & ((1u << sub) - 1u))] = make_int2(code, stack_key(key));
+                if (key != kNoKey && sub != sel) stack_store(stk + 8u * (unsigned)(sp + __popc(others & below)), code, (int)(key & 0x7ffffff8u));
                 sp += __popc(others);
             }
-            __syncwarp();                                              // stack writes visible to the group before any later pop
-            // leaves with candidates: verify the closest against the reference's node chain; on a rejection try the next one
-            bool pending = leaf && hit_bits != 0u;
-            while (__any_sync(kFullMask, pending)) {
-                if (__any_sync(kFullMask, pending && (sel_bits & (sel_bits - 1u)) != 0u)) {     // equal t inside a leaf: lower rank first
-                    const int rmin = group_min((flag && key == kmin) ? rank : 0x7fffffff);
-                    sel_bits = (__ballot_sync(kFullMask, flag && key == kmin && rank == rmin) >> gbase) & 0xffu;
-                    sel = sel_bits ? __ffs(sel_bits) - 1 : 0;
-                }
-                bool accepted = false;
-                if (pending && sub == sel) {
-                    accepted = reference_tests_node(P, o, d, s, ref, whole_chain);
-                    flag = false; key = m_huge<R>();                   // consumed either way
-                }
-                const unsigned acc_bits = (__ballot_sync(kFullMask, accepted) >> gbase) & 0xffu;
-                const R wt = kmin;                                   // (uniform in the group)
-                const R wu = __shfl_sync(kFullMask, tu, gbase + sel), wv = __shfl_sync(kFullMask, tv, gbase + sel);
-                const int wrank = __shfl_sync(kFullMask, rank, gbase + sel), wslot = __shfl_sync(kFullMask, slot, gbase + sel);
-                if (pending && acc_bits) { ct = wt; crank = wrank; cslot = wslot; cu = wu; cv = wv; pending = false; }
-                // rejected: the remaining candidates of this leaf
-                kmin = group_min(key);
-                sel_bits = (__ballot_sync(kFullMask, flag && key == kmin) >> gbase) & 0xffu;
-                sel = sel_bits ? __ffs(sel_bits) - 1 : 0;
-                if (sel_bits == 0u) pending = false;
+            // accepted triangle candidates: closest, then lowest rank
+            if (__any_sync(kFullMask, cand)) {
+                const R tbest = group_min(cand ? tt : m_huge<R>());
+                const int rmin = group_min((cand && tt == tbest) ? (rank << 3) | sub : 0x7fffffff);
+                const int src = gbase + (rmin & 7);
+                const R wu = __shfl_sync(kFullMask, tu, src), wv = __shfl_sync(kFullMask, tv, src);
+                const int wslot = __shfl_sync(kFullMask, slot, src);
+                if (rmin != 0x7fffffff) { ct = tbest; crank = rmin >> 3; cslot = wslot; cu = wu; cv = wv; }
             }
+            __syncwarp();                                              // stack writes visible to the group before any later pop
             if (cur != kDone && next == kDone) {                      // pop; children beyond the current best are dropped
                 const R lim2 = ct * R(1.0001);
                 while (sp > 0) {
                     --sp;
-                    const int2 e = stk[sp];
+                    const int2 e = stack_load(stk + 8u * (unsigned)sp);
                     if (!(R(__int_as_float(e.y)) > lim2)) { next = e.x; break; }
                 }
             }
@@ -591,7 +596,7 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& o
 
 // All mesh objects of the scene (tracer.cl:598-720), after the analytic objects.  Called by all 32 lanes.
 template <typename R>
-__device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h, int2* __restrict__ stk) {
+__device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h, unsigned stk) {
     {
         for (int q = 0; q < P.n_mesh; ++q) {
             const int j = P.mesh_obj[q];
@@ -963,6 +968,7 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
     // pure function of (seed, sample, bounce), so evaluation order does not change any value.
     __shared__ R next_ray[6][kBlockThreads];          // the parked ray: written once and read once per path, so not in registers
     bool have_next = false;
+    const unsigned stack_base = GROUPS ? (unsigned)__cvta_generic_to_shared(mesh_stacks) + (threadIdx.x / kWide) * (unsigned)P.stack_entries * 8u : 0u;
 
     while (true) {
         if (fresh && s.n >= n_end) live = false;
@@ -989,7 +995,7 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
 
         Hit<R> h;
         closest_analytic<R>(P, s.ro, s.rd, h);
-        if (GROUPS) closest_mesh<R>(P, s.ro, s.rd, live, lane, h, mesh_stacks + (threadIdx.x / kWide) * P.stack_entries);
+        if (GROUPS) closest_mesh<R>(P, s.ro, s.rd, live, lane, h, stack_base);
 
         bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
         if (live && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);

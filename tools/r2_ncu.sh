@@ -8,8 +8,8 @@ for W in "$@"; do
   case $W in
     ref) CMD="python tools/r2_time.py ref"; export SPP_SCALE=0.03125;;
     ref64) CMD="python tools/r2_time.py ref64"; export SPP_SCALE=0.0625;;
-    teapot) CMD="python tools/r2_time.py teapot"; export SPP_SCALE=0.015625;;
-    gopher) CMD="python tools/r2_time.py gopher"; export SPP_SCALE=0.015625;;
+    teapot) CMD="python tools/r2_time.py teapot"; export SPP_SCALE=0.125;;
+    gopher) CMD="python tools/r2_time.py gopher"; export SPP_SCALE=0.125;;
     cube) CMD="python tools/r2_time.py cube"; export SPP_SCALE=0.0625;;
     tex) CMD="python tools/r2_time.py tex"; export SPP_SCALE=0.0625;;
   esac
