@@ -38,7 +38,7 @@
 #include "rng.cuh"
 
 #ifndef PTK_KERNEL_VERSION
-#define PTK_KERNEL_VERSION "r02v1"      // names the ncu captures under profiles/ that belong to this kernel source
+#define PTK_KERNEL_VERSION "r02v4"      // names the ncu captures under profiles/ that belong to this kernel source
 #endif
 
 namespace ptk {
@@ -194,6 +194,8 @@ template <typename R> struct Params {
     int fast_obj[kFastSlots];   // slot -> object index
     DObjHot<R> hot[kMaxObjects];    // read by the slow loop and the mesh walk only
     int slow_obj[kMaxObjects];  int n_slow;    // analytic objects outside the fast slots (general spheres, cylinders, cubes, overflow), scene order
+    int slow_kind[kMaxObjects];                // 3: by its hot record; 0 plane / 1 similarity sphere / 2 ellipsoid: by slow_rec, with the slots' arithmetic
+    DFast<R> slow_rec[kMaxObjects], slow_rec2[kMaxObjects];
     int mesh_obj[kMaxObjects];  int n_mesh;    // group objects with triangles, scene order
     const DObjShade<R>* shade;  int n_objects;
     // reference BVH (the caller's groups) re-emitted in the reference's visiting order: only the boxes and the
@@ -205,7 +207,7 @@ template <typename R> struct Params {
     // wide[(n*8+c)*2+1] = (hi.xyz, -): padded box of the child.  Code >= 0: inner node; kEmptyChild: no child;
     // otherwise a leaf, ~code = (first slot << 4) | triangle count (<= 8).
     const V4<R>* wide;
-    const DMesh<R>* mesh;       // per object (valid for groups)
+    DMesh<R> mesh[kMaxObjects]; // per object (valid for groups)
     const int2* tri_info;       // per slot: (rank in the reference's recording order, reference node)
     const V4<R>* tri_test;      // 3 per slot: (p1.xyz,e1.x) (e1.yz,e2.xy) (e2.z,-,-,-)
     const V4<R>* tri_shade;     // 3 per slot: (n1.xyz,col.r) (n2.xyz,col.g) (n3.xyz,col.b)
@@ -621,38 +623,53 @@ template <typename R> __device__ __forceinline__ void offer_ordered(Hit<R>& h, R
     if (t > eps && (t < h.t || (t == h.t && obj < h.obj))) { h.t = t; h.obj = obj; }
 }
 
-// Fast slots, unrolled (see DFast).  `a` = dot(rd, rd) and `inv_a` = 1 / a are per-ray values shared by every sphere
-// slot.  The winner is tracked as a SLOT number (an immediate); closest_analytic maps it to the object index once.
-template <typename R> __device__ __forceinline__ R fma3(R a, R x, R b, R y, R c, R z, R d) { return a * x + (b * y + (c * z + d)); }
+// Fast objects (see DFast).  The arithmetic is spelled with explicit fused multiply-adds and shared by the unrolled
+// slots and the slow loop's overflow entries, so an object gives bit-identical t on either path: coincident objects
+// (two coplanar planes, a duplicated sphere) tie EXACTLY wherever they land, and the tie goes to the lower index as
+// upstream.  `a` = dot(rd, rd) and `inv_a` = 1 / a are per-ray values shared by every similarity sphere.
+__device__ __forceinline__ float m_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double m_fma(double a, double b, double c) { return fma(a, b, c); }
 // sqrt(disc) for disc > 0, NaN otherwise (the reference records roots only when disc > 0, tracer.cl:465): in float
 // disc * rsqrt(disc) does it without a compare -- rsqrt(0) = inf, inf * 0 = NaN, rsqrt(negative) = NaN
 __device__ __forceinline__ float sqrt_pos(float disc) { return disc * m_rsqrt(disc); }
 __device__ __forceinline__ double sqrt_pos(double disc) { return disc > 0.0 ? sqrt(disc) : __longlong_as_double(0x7ff8000000000000LL); }
 
+// plane, tracer.cl:478-483: t = -o'.y / d'.y, valid when |d'.y| > EPSILON (`dy` returned for that test)
+template <typename R> __device__ __forceinline__ R plane_t(const DFast<R>& f, V3<R> ro, V3<R> rd, R& dy) {
+    const R oy = m_fma(f.a, ro.x, m_fma(f.b, ro.y, m_fma(f.c, ro.z, f.d)));
+    dy = m_fma(f.a, rd.x, m_fma(f.b, rd.y, f.c * rd.z));
+    return -oy * m_rcp(dy);
+}
+// sphere, tracer.cl:448-476 (both roots recorded when disc > 0): returns the first root beyond EPSILON -- the pair's
+// winner since t0 <= t1 -- and the larger root in `t1`; without real roots both are NaN and fail every comparison
+template <typename R> __device__ __forceinline__ R sphere_t(const DFast<R>& f, const DFast<R>& g, int kind, V3<R> ro, V3<R> rd, R a, R inv_a, R eps, R& t1) {
+    V3<R> oc = {ro.x - f.a, ro.y - f.b, ro.z - f.c}, dd = rd;
+    R c1 = f.d;
+    if (kind != 0) {                                             // ellipsoid: scale the offset and the direction, own a and 1/a
+        oc = {oc.x * g.a, oc.y * g.b, oc.z * g.c};
+        dd = {rd.x * g.a, rd.y * g.b, rd.z * g.c};
+        a = m_fma(dd.x, dd.x, m_fma(dd.y, dd.y, dd.z * dd.z)); inv_a = m_rcp(a); c1 = R(1);
+    }
+    const R hb = m_fma(dd.x, oc.x, m_fma(dd.y, oc.y, dd.z * oc.z));
+    const R c = m_fma(oc.x, oc.x, m_fma(oc.y, oc.y, m_fma(oc.z, oc.z, -c1)));
+    const R sq = sqrt_pos(m_fma(hb, hb, -(a * c)));
+    const R t0 = (-hb - sq) * inv_a;
+    t1 = (-hb + sq) * inv_a;
+    return t0 > eps ? t0 : t1;
+}
+
+// Unrolled slots.  The winner is tracked as a SLOT number (an immediate); closest_analytic maps it to the object index once.
 template <typename R, int SLOT>
 __device__ __forceinline__ void fast_plane(const Params<R>& P, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
-    const DFast<R>& f = P.fast[SLOT];                            // tracer.cl:478-483: t = -o'.y / d'.y when |d'.y| > EPSILON
-    const R oy = fma3(f.a, ro.x, f.b, ro.y, f.c, ro.z, f.d);
-    const R dy = fma3(f.a, rd.x, f.b, rd.y, f.c, rd.z, R(0));
-    const R t = -oy * m_rcp(dy);
+    R dy;
+    const R t = plane_t(P.fast[SLOT], ro, rd, dy);
     if (m_abs(dy) > eps && t > eps && t < h.t) { h.t = t; h.obj = SLOT; }
 }
 template <typename R, int SLOT>
 __device__ __forceinline__ void fast_sphere(const Params<R>& P, V3<R> ro, V3<R> rd, R a, R inv_a, R eps, Hit<R>& h) {
-    const DFast<R>& f = P.fast[SLOT];                            // tracer.cl:448-476: both roots recorded when disc > 0
-    V3<R> oc = {ro.x - f.a, ro.y - f.b, ro.z - f.c}, dd = rd;
-    R c1 = f.d;
-    if (P.fast_kind[SLOT] != 0) {                                // ellipsoid: scale the offset and the direction, own a and 1/a
-        const DFast<R>& g = P.fast2[SLOT];
-        oc = {oc.x * g.a, oc.y * g.b, oc.z * g.c};
-        dd = {rd.x * g.a, rd.y * g.b, rd.z * g.c};
-        a = dot(dd, dd); inv_a = m_rcp(a); c1 = R(1);
-    }
-    const R hb = dot(dd, oc), c = dot(oc, oc) - c1;
-    const R sq = sqrt_pos(hb * hb - a * c);
-    const R t0 = (-hb - sq) * inv_a, t1 = (-hb + sq) * inv_a;    // t0 <= t1: the first root beyond EPSILON is the pair's winner
-    const R t = t0 > eps ? t0 : t1;
-    if (t1 > eps && t < h.t) { h.t = t; h.obj = SLOT; }          // (NaN roots fail every comparison)
+    R t1;
+    const R t = sphere_t(P.fast[SLOT], P.fast2[SLOT], P.fast_kind[SLOT], ro, rd, a, inv_a, eps, t1);
+    if (t1 > eps && t < h.t) { h.t = t; h.obj = SLOT; }
 }
 template <typename R, int K, int END>
 __device__ __forceinline__ void run_planes(const Params<R>& P, int n, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
@@ -721,14 +738,23 @@ template <typename R>
 __device__ __forceinline__ void closest_analytic(const Params<R>& P, V3<R> ro, V3<R> rd, Hit<R>& h) {
     const R eps = P.eps;
     h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
-    const R a = dot(rd, rd), inv_a = m_rcp(a);
+    const R a = m_fma(rd.x, rd.x, m_fma(rd.y, rd.y, rd.z * rd.z)), inv_a = m_rcp(a);
     run_spheres<R, 0, 0, kFastA>(P, P.fast_n[0], ro, rd, a, inv_a, eps, h);
     run_planes<R, kFastA, kFastA + kFastB>(P, P.fast_n[1], ro, rd, eps, h);
     run_spheres<R, kFastA + kFastB, kFastA + kFastB, kFastSlots>(P, P.fast_n[2], ro, rd, a, inv_a, eps, h);
     if (h.obj >= 0) h.obj = P.fast_obj[h.obj];                   // slot -> object index
     for (int k = 0; k < P.n_slow; ++k) {
-        const int j = P.slow_obj[k];
-        test_object<R>(P.hot[j], j, P.hot[j].type, ro, rd, eps, h);
+        const int j = P.slow_obj[k], kind = P.slow_kind[k];
+        if (kind == 3) test_object<R>(P.hot[j], j, P.hot[j].type, ro, rd, eps, h);
+        else if (kind == 0) {                                    // a plane beyond the unrolled slots: same arithmetic as there
+            R dy;
+            const R t = plane_t(P.slow_rec[k], ro, rd, dy);
+            if (m_abs(dy) > eps) offer_ordered(h, t, j, eps);
+        } else {                                                 // a fast-class sphere beyond the unrolled slots
+            R t1;
+            const R t = sphere_t(P.slow_rec[k], P.slow_rec2[k], kind - 1, ro, rd, a, inv_a, eps, t1);
+            if (t1 > eps) offer_ordered(h, t, j, eps);
+        }
     }
 }
 
@@ -968,7 +994,8 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
     // pure function of (seed, sample, bounce), so evaluation order does not change any value.
     __shared__ R next_ray[6][kBlockThreads];          // the parked ray: written once and read once per path, so not in registers
     bool have_next = false;
-    const unsigned stack_base = GROUPS ? (unsigned)__cvta_generic_to_shared(mesh_stacks) + (threadIdx.x / kWide) * (unsigned)P.stack_entries * 8u : 0u;
+    unsigned stack_base = GROUPS ? (unsigned)__cvta_generic_to_shared(mesh_stacks) + (threadIdx.x / kWide) * (unsigned)P.stack_entries * 8u : 0u;
+    asm volatile("" : "+r"(stack_base));      // opaque: keep it in a register instead of re-deriving the shared window base at every pop
 
     while (true) {
         if (fresh && s.n >= n_end) live = false;

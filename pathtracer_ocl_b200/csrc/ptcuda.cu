@@ -60,7 +60,8 @@ template <typename R> struct HostScene {
     ptk::DFast<R> fast[ptk::kFastSlots];
     ptk::DFast<R> fast2[ptk::kFastSlots];
     int fast_n[4], fast_obj[ptk::kFastSlots], fast_kind[ptk::kFastSlots];
-    int slow_obj[ptk::kMaxObjects], n_slow = 0;
+    int slow_obj[ptk::kMaxObjects], slow_kind[ptk::kMaxObjects], n_slow = 0;
+    ptk::DFast<R> slow_rec[ptk::kMaxObjects], slow_rec2[ptk::kMaxObjects];
     int mesh_obj[ptk::kMaxObjects], n_mesh = 0;
     int stack_need = 0;        // deepest deferred-child stack any mesh of the scene can need
     std::vector<ptk::DObjShade<R>> shade;
@@ -447,6 +448,7 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
     // fast slots -- three runs "spheres, planes, spheres" filled greedily in scene order, so fast objects keep their
     // relative order; other analytic objects take the slow loop; groups with triangles the mesh walk.
     out.n_slow = out.n_mesh = 0;
+    std::memset(out.slow_kind, 0, sizeof out.slow_kind); std::memset(out.slow_rec, 0, sizeof out.slow_rec); std::memset(out.slow_rec2, 0, sizeof out.slow_rec2);
     for (int k = 0; k < 4; ++k) out.fast_n[k] = 0;
     for (int k = 0; k < ptk::kFastSlots; ++k) {
         out.fast_obj[k] = -1; out.fast_kind[k] = 0;
@@ -493,7 +495,13 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
             else if (out.fast_n[2] < run_cap[2]) { run = 2; slot = run_begin[2] + out.fast_n[2]++; }
         }
         if (slot >= 0) { out.fast[slot] = rec; out.fast2[slot] = rec2; out.fast_kind[slot] = kind; out.fast_obj[slot] = i; }
-        else out.slow_obj[out.n_slow++] = i;
+        else {
+            // overflow (a full run, or an order that does not fit "spheres, planes, spheres"): fast-class objects keep
+            // their record and the slots' arithmetic in the slow loop, so coincident objects still tie exactly
+            out.slow_kind[out.n_slow] = want == 1 ? 0 : want == 0 ? 1 + kind : 3;
+            out.slow_rec[out.n_slow] = rec; out.slow_rec2[out.n_slow] = rec2;
+            out.slow_obj[out.n_slow++] = i;
+        }
     }
     const auto* cam = static_cast<const ptw_camera*>(job.camera);
     out.cam.pixel_size = R(cam->pixel_size); out.cam.half_width = R(cam->half_width); out.cam.half_height = R(cam->half_height);
@@ -526,7 +534,7 @@ struct DeviceState {
     std::vector<int> rows;          // frame rows owned by this device, increasing
     std::vector<void*> allocs;      // everything allocated on this device
     cudaMemPool_t pool = nullptr;   // stream-ordered pool (single-GPU contexts), else plain cudaMalloc
-    void* shade = nullptr; void* lens = nullptr; void* mesh = nullptr;
+    void* shade = nullptr; void* lens = nullptr;
     void* node_lo = nullptr; void* node_hi = nullptr; void* node_parent = nullptr;
     void* wide = nullptr;
     void* tri_test = nullptr; void* tri_shade = nullptr; void* tri_info = nullptr;
@@ -624,7 +632,6 @@ template <typename R> void upload_scene(DeviceState& d, const HostScene<R>& s, i
     d.node_lo = upload(d, s.node_lo, h2d);
     d.node_hi = upload(d, s.node_hi, h2d);
     d.node_parent = upload(d, s.node_parent, h2d);
-    d.mesh = upload(d, s.mesh, h2d);
     d.wide = upload(d, s.wide, h2d);
     d.tri_test = upload(d, s.tri_test, h2d);
     d.tri_shade = upload(d, s.tri_shade, h2d);
@@ -672,6 +679,9 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     std::memcpy(P.fast_kind, s.fast_kind, sizeof P.fast_kind);
     std::memcpy(P.fast_obj, s.fast_obj, sizeof P.fast_obj);
     std::memcpy(P.slow_obj, s.slow_obj, sizeof P.slow_obj);
+    std::memcpy(P.slow_kind, s.slow_kind, sizeof P.slow_kind);
+    std::memcpy(P.slow_rec, s.slow_rec, sizeof P.slow_rec);
+    std::memcpy(P.slow_rec2, s.slow_rec2, sizeof P.slow_rec2);
     std::memcpy(P.mesh_obj, s.mesh_obj, sizeof P.mesh_obj);
     P.n_slow = s.n_slow; P.n_mesh = s.n_mesh;
     P.stack_entries = (s.stack_need + 1) | 1;          // odd: the four groups of a warp push to different banks
@@ -681,7 +691,7 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     P.node_lo = static_cast<const ptk::V4<R>*>(d.node_lo);
     P.node_hi = static_cast<const ptk::V4<R>*>(d.node_hi);
     P.node_parent = static_cast<const int*>(d.node_parent);
-    P.mesh = static_cast<const ptk::DMesh<R>*>(d.mesh);
+    for (int k = 0; k < c.n_objects; ++k) P.mesh[k] = s.mesh[size_t(k)];
     P.wide = static_cast<const ptk::V4<R>*>(d.wide);
     P.tri_test = static_cast<const ptk::V4<R>*>(d.tri_test);
     P.tri_shade = static_cast<const ptk::V4<R>*>(d.tri_shade);
