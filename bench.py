@@ -90,6 +90,22 @@ def workload_name(scene, w, h, spp, ap, fl, label=None):
     return f"{s} ({label})" if label else s
 
 
+class quiet_stdout:
+    """The reference kernel prints debug lines for one hard-coded pixel (tracer.cl:1131-1134, printf from device code;
+    the CPU build inherits them): keep them out of this program's stdout, which carries the JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self._saved, 1)
+        os.close(self._null)
+        os.close(self._saved)
+
+
 # ---- CPU arm (oracle/ is allowed here as the timed baseline only) ----------------------------------------
 # Two CPU implementations of the path exist: oracle/_ref -- the reference's OWN kernel source (tracer.cl) compiled for
 # the host CPU through oracle/cl_shim.hpp, kind "reference" -- and the oracle, a restatement of it (kind "port") that also
@@ -105,7 +121,10 @@ def cpu_kernel(scene, seeds, threads, spp_probe, counters=None):
         counters = O.trace(scene, seeds, max(1, spp_probe), precision=1, nthreads=threads)[1]
     fits = counters["max_intersections"] <= 56
     if fits and O.ref_lib() is not None:
-        return (lambda scene, seeds, spp, threads: O.ref_trace(scene, seeds, spp, nthreads=threads), "reference",
+        def run_ref(scene, seeds, spp, threads):
+            with quiet_stdout():
+                return O.ref_trace(scene, seeds, spp, nthreads=threads)
+        return (run_ref, "reference",
                 "the reference's own kernel source (internal/ocl/tracer.cl) compiled for the host CPU through oracle/cl_shim.hpp "
                 "(scalar g++ -O2 -ffp-contract=off, canonical double-precision sin, the kernel's debug printf live), "
                 "work-items spread over all host threads; no OpenCL runtime exists in this image")

@@ -32,10 +32,10 @@ def lib() -> C.CDLL:
             build()
         L = C.CDLL(_LIB_PATH)
         L.oracle_counter_name.restype = C.c_char_p
-        L.oracle_trace2.restype = C.c_int
-        L.oracle_trace2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+        L.oracle_trace3.restype = C.c_int
+        L.oracle_trace3.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                    C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p]
         L.oracle_noise3d_array_mode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_noise3d.restype = C.c_float
@@ -61,8 +61,11 @@ def counter_names():
     return [L.oracle_counter_name(i).decode() for i in range(L.oracle_counter_count())]
 
 
+NEE, CYLINDER_CAPS = 1, 2      # `features` bits: the code paths the reference ships commented out (tracer.cl:1168, :437-444)
+
+
 def trace(scene, seeds: np.ndarray, samples: int, precision: int = 1, rows: Optional[Tuple[int, int]] = None,
-          nthreads: Optional[int] = None, rng_mode: int = 0) -> Tuple[np.ndarray, Dict[str, int]]:
+          nthreads: Optional[int] = None, rng_mode: int = 0, features: int = 0) -> Tuple[np.ndarray, Dict[str, int]]:
     """Render rows [rows[0], rows[1]) of `scene` (a pathtracer_ocl_b200.scene.SceneBuffers).
 
     Returns (rgba float64 [nrows, W, 4], event counters)."""
@@ -85,10 +88,10 @@ def trace(scene, seeds: np.ndarray, samples: int, precision: int = 1, rows: Opti
             ptrs[c] = t.ctypes.data
             tl[c], th[c], tw[c] = t.shape[0], t.shape[1], t.shape[2]
     counters = np.zeros(L.oracle_counter_count(), dtype=np.uint64)
-    rc = L.oracle_trace2(scene.objects.ctypes.data, scene.n_objects,
-                        scene.triangles.ctypes.data if scene.n_triangles else None, scene.n_triangles,
-                        scene.groups.ctypes.data if scene.n_groups else None, scene.n_groups,
-                        scene.camera.ctypes.data, ptrs, tw, th, tl, seeds.ctypes.data, samples, precision, rng_mode, r0, r1,
+    rc = L.oracle_trace3(scene.objects.ctypes.data, scene.n_objects,
+                         scene.triangles.ctypes.data if scene.n_triangles else None, scene.n_triangles,
+                         scene.groups.ctypes.data if scene.n_groups else None, scene.n_groups,
+                         scene.camera.ctypes.data, ptrs, tw, th, tl, seeds.ctypes.data, samples, precision, rng_mode, features, r0, r1,
                          nthreads, out.ctypes.data, counters.ctypes.data)
     if rc != 0:
         raise RuntimeError(f"oracle_trace failed with code {rc}")
@@ -113,18 +116,19 @@ def model_flops(counters: Dict[str, int], dof: bool = False) -> float:
 
 
 # ---- the reference's own kernel, compiled for the CPU (oracle/build_ref.py) -----------------------------------------
-_ref_lib = None
+_ref_libs: Dict[int, Optional[C.CDLL]] = {}
 
 
-def ref_lib() -> Optional[C.CDLL]:
-    """oracle/_ref/libtracer_ref.so: /root/reference/internal/ocl/tracer.cl compiled as C++ through cl_shim.hpp.
+def ref_lib(features: int = 0) -> Optional[C.CDLL]:
+    """oracle/_ref/libtracer_ref.so: /root/reference/internal/ocl/tracer.cl compiled as C++ through cl_shim.hpp
+    (features != 0: the variant with the NEE call / the cylinder caps un-commented, libtracer_ref_f<features>.so).
     Built here when the reference source is present; elsewhere (the GPU box) the prebuilt library is used; None if
     neither exists."""
-    global _ref_lib
-    if _ref_lib is None:
+    if features not in _ref_libs:
         from . import build_ref
-        path = build_ref.build()
+        path = build_ref.build(features=features)
         if not path:
+            _ref_libs[features] = None
             return None
         L = C.CDLL(path)
         L.ref_trace.restype = C.c_int
@@ -133,8 +137,8 @@ def ref_lib() -> Optional[C.CDLL]:
                                 C.c_int, C.c_int, C.c_void_p]
         L.ref_closest.restype = C.c_int
         L.ref_closest.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
-        _ref_lib = L
-    return _ref_lib
+        _ref_libs[features] = L
+    return _ref_libs[features]
 
 
 def ref_closest(scene, rays: np.ndarray) -> np.ndarray:
@@ -152,9 +156,9 @@ def ref_closest(scene, rays: np.ndarray) -> np.ndarray:
 
 
 def ref_trace(scene, seeds: np.ndarray, samples: int, rows: Optional[Tuple[int, int]] = None,
-              nthreads: Optional[int] = None) -> np.ndarray:
+              nthreads: Optional[int] = None, features: int = 0) -> np.ndarray:
     """Rows [rows[0], rows[1]) of `scene` rendered by the REFERENCE kernel itself (fp64, canonical sin).  [nrows, W, 4]."""
-    L = ref_lib()
+    L = ref_lib(features)
     if L is None:
         raise RuntimeError("the compiled reference kernel is not available (no /root/reference and no oracle/_ref/libtracer_ref.so)")
     W, H = scene.width, scene.height

@@ -66,6 +66,7 @@ template <typename Real> inline V4<Real> mul(const M16<Real>& a, V4<Real> v) {
 }
 
 template <typename Real> struct Obj {   // tracer.cl:37-63, converted once to Real
+    M16<Real> transform;
     M16<Real> inverse, inverse_transpose;
     V4<Real> color, emission, bb_min, bb_max;
     Real refractive_index, min_y, max_y, reflectivity, tsx, tsy, tsx_nm, tsy_nm;
@@ -89,6 +90,7 @@ template <typename Real> struct Scene {
     Texture tex[3];
     unsigned samples;
     int rng_fast;   // 0: correctly rounded sine (parity stream); 1: the reproducible fast stream (canon_rng.h)
+    int features;   // bit 0: next-event estimation (tracer.cl:1168 un-commented), bit 1: cylinder caps (tracer.cl:437-444 un-commented)
     Real PI, EPSILON;
 };
 
@@ -270,7 +272,7 @@ struct Tracer {
                 if (t2 != Real(0.0)) ctx.push(t2, j);
             } else if (ob.type == 2) {                            // cylinder side, tracer.cl:396-446
                 cnt[C_OBJ_CYL]++;
-                Real out0 = 0, out1 = 0;
+                Real out0 = 0, out1 = 0, out2 = 0, out3 = 0;
                 Real rdx2 = d.x * d.x, rdz2 = d.z * d.z;
                 Real a = rdx2 + rdz2;
                 if (!(std::fabs(a) < EPS)) {
@@ -285,10 +287,27 @@ struct Tracer {
                         if (y0 > ob.min_y && y0 < ob.max_y) out0 = t0;
                         Real y1 = o.y + t1 * d.y;
                         if (y1 > ob.min_y && y1 < ob.max_y) out1 = t1;
+                        if (sc.features & 2) {                    // tracer.cl:437-444 enabled: intersectCaps, :290-310
+                            Real cx = 0, cy = 0;
+                            if (!(std::fabs(d.y) < EPS)) {
+                                auto check_cap = [&](Real t) {   // tracer.cl:282-286
+                                    Real x = o.x + t * d.x, z = o.z + t * d.z;
+                                    return x * x + z * z <= Real(1.0);
+                                };
+                                Real tc1 = (ob.min_y - o.y) / d.y;
+                                if (check_cap(tc1)) cx = tc1;
+                                Real tc2 = (ob.max_y - o.y) / d.y;
+                                if (check_cap(tc2)) cy = tc2;
+                            }
+                            if (cx > Real(0.0)) out2 = cx;
+                            if (cy > Real(0.0)) out3 = cy;
+                        }
                     }
                 }
                 if (out0 != Real(0)) ctx.push(out0, j);
                 if (out1 != Real(0)) ctx.push(out1, j);
+                if (out2 != Real(0)) ctx.push(out2, j);
+                if (out3 != Real(0)) ctx.push(out3, j);
             } else if (ob.type == 3) {                            // cube, tracer.cl:378-394
                 cnt[C_OBJ_CUBE]++;
                 Real x0, x1, y0, y1, z0, z1;
@@ -395,7 +414,47 @@ struct Tracer {
         return u * std::cos(rand1) * rand2s + v * std::sin(rand1) * rand2s + n * std::sqrt(Real(1.0) - rand2);
     }
 
-    struct Bounce { V4<Real> color, emission; Real cos; bool is_refraction; };
+    struct Bounce { V4<Real> point, color, emission, normal; Real cos; bool is_refraction; };
+
+    // tracer.cl:321-336 (sic: the latitude is shifted by 2*PI and y by PI/4 -- kept as written)
+    V4<Real> random_point_on_sphere(Real r, Real u1, Real u2) {
+        Real lat = std::acos(Real(2) * u1 - Real(1)) - sc.PI * Real(2);
+        Real lon = Real(2) * sc.PI * u2;
+        V4<Real> out = {0, 0, 0, Real(1.0)};
+        out.x = std::cos(lat) * std::cos(lon) * r;
+        out.y = (std::sin(lat) - sc.PI * Real(0.25)) * r;
+        out.z = std::cos(lat) * std::sin(lon) * r;
+        return out;
+    }
+
+    // tracer.cl:786-825, called from the shading loop when the feature is on (the call upstream keeps commented out, :1168)
+    void next_event_estimation(const Bounce& b, float fgi_f, float fgi2_f, unsigned n_u, V4<Real> mask, unsigned x, V4<Real>& accum) {
+        const Real EPS = sc.EPSILON;
+        const Real fgi = Real(fgi_f), fgi2 = Real(fgi2_f), n = Real(n_u);       // the kernel's `double` parameters
+        for (unsigned l = 0; l < sc.objects.size(); ++l) {
+            const Obj<Real>& light = sc.objects[l];
+            if (!(light.emission.x > Real(0.0))) continue;
+            V4<Real> light_origin = {light.transform.m[3], light.transform.m[7], light.transform.m[11], Real(0.0)};
+            Real scale_by = std::fmax(std::fmax(light.transform.m[0], light.transform.m[5]), light.transform.m[10]);
+            V4<Real> light_scale = {scale_by, scale_by, scale_by, Real(1.0)};
+            float r1 = noise(float(fgi), float(n + Real(x * l)), float(fgi2));
+            float r2 = noise(float(fgi), float(fgi2), float(n + Real(x * x * l)));
+            V4<Real> rpos = random_point_on_sphere(Real(1.0), Real(r1), Real(r2));
+            V4<Real> light_position = light_origin + (rpos * light_scale);
+            V4<Real> dir = normalize(light_position - b.point);
+            V4<Real> origin = b.point + (dir * EPS);
+            Real light_dot_normal = dot(dir, b.normal);
+            if (light_dot_normal > Real(0.0)) {
+                Real t; int slot;
+                int hit = closest(origin, dir, t, slot);
+                if (hit == int(l) && t > EPS) {
+                    V4<Real> effective = b.color * light.emission;
+                    Real attenuation = Real(1) - t / std::sqrt(t * t + light.transform.m[0] * light.transform.m[0]);
+                    accum = accum + effective * light_dot_normal * mask * attenuation;
+                }
+            }
+        }
+    }
 
     // tracer.cl:831-1187, one pixel
     void pixel(unsigned x, unsigned y, double seed, double* out) {
@@ -500,6 +559,8 @@ struct Tracer {
                 }
                 ro = over;
                 Bounce bn;
+                bn.point = position;
+                bn.normal = nv;
                 bn.cos = cosine;
                 bn.is_refraction = entering || exiting;
                 if (ob.type == 4) {
@@ -548,6 +609,7 @@ struct Tracer {
                     if (k == 0) accum = bn.color;
                     break;
                 }
+                if (sc.features & 1) next_event_estimation(bn, fgi, fgi2, n, mask, k, accum);   // tracer.cl:1168
                 mask = mask * bn.color;
                 mask = mask * bn.cos;
             }
@@ -563,14 +625,16 @@ struct Tracer {
 template <typename Real>
 void build_scene(Scene<Real>& sc, const ptw_object* objs, int n_obj, const ptw_triangle* tris, int n_tri, const ptw_group* groups,
                  int n_grp, const ptw_camera* cam, const uint8_t* const* tex, const int32_t* tw, const int32_t* th,
-                 const int32_t* tl, int samples, int rng_fast) {
+                 const int32_t* tl, int samples, int rng_fast, int features) {
     sc.rng_fast = rng_fast;
+    sc.features = features;
     sc.PI = Real(double(3.14159265359f));    // tracer.cl:1
     sc.EPSILON = Real(0.0001);               // tracer.cl:4
     sc.samples = unsigned(samples);
     for (int i = 0; i < n_obj; ++i) {
         const ptw_object& s = objs[i];
         Obj<Real> o;
+        o.transform = cm16<Real>(s.transform);
         o.inverse = cm16<Real>(s.inverse);
         o.inverse_transpose = cm16<Real>(s.inverse_transpose);
         o.color = cv4<Real>(s.color); o.emission = cv4<Real>(s.emission);
@@ -609,9 +673,9 @@ void build_scene(Scene<Real>& sc, const ptw_object* objs, int n_obj, const ptw_t
 template <typename Real>
 int run(const ptw_object* objs, int n_obj, const ptw_triangle* tris, int n_tri, const ptw_group* groups, int n_grp,
         const ptw_camera* cam, const uint8_t* const* tex, const int32_t* tw, const int32_t* th, const int32_t* tl,
-        const double* seeds, int samples, int rng_fast, int row0, int row1, int nthreads, double* out, uint64_t* counters) {
+        const double* seeds, int samples, int rng_fast, int features, int row0, int row1, int nthreads, double* out, uint64_t* counters) {
     Scene<Real> sc;
-    build_scene(sc, objs, n_obj, tris, n_tri, groups, n_grp, cam, tex, tw, th, tl, samples, rng_fast);
+    build_scene(sc, objs, n_obj, tris, n_tri, groups, n_grp, cam, tex, tw, th, tl, samples, rng_fast, features);
     const int W = cam->width;
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(row0);
@@ -657,9 +721,10 @@ const char* oracle_counter_name(int i) {
 // Renders rows [row0,row1) of the frame.  precision: 0 = float arithmetic, 1 = double (tracer.cl).
 // rng_mode: 0 = parity stream, 1 = fast stream (both defined in canon_rng.h).
 // seeds: width*height doubles (whole frame).  out: (row1-row0)*width*4 doubles.
-int oracle_trace2(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,
+// features: bit 0 next-event estimation, bit 1 cylinder caps -- the two code paths the reference ships switched off.
+int oracle_trace3(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,
                   const void* camera, const uint8_t* const* tex, const int32_t* tex_w, const int32_t* tex_h,
-                  const int32_t* tex_layers, const double* seeds, int samples, int precision, int rng_mode, int row0, int row1,
+                  const int32_t* tex_layers, const double* seeds, int samples, int precision, int rng_mode, int features, int row0, int row1,
                   int nthreads, double* out, uint64_t* counters) {
     if (!objects || n_objects < 1 || n_objects > PTW_MAX_OBJECTS || !camera || !seeds || !out || samples < 1) return 1;
     const ptw_camera* cam = static_cast<const ptw_camera*>(camera);
@@ -668,8 +733,16 @@ int oracle_trace2(const void* objects, int n_objects, const void* triangles, int
     auto* t = static_cast<const ptw_triangle*>(triangles);
     auto* g = static_cast<const ptw_group*>(groups);
     const int fast = rng_mode != 0;
-    if (precision == 1) return run<double>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, fast, row0, row1, nthreads, out, counters);
-    return run<float>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, fast, row0, row1, nthreads, out, counters);
+    if (precision == 1) return run<double>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, fast, features, row0, row1, nthreads, out, counters);
+    return run<float>(o, n_objects, t, n_triangles, g, n_groups, cam, tex, tex_w, tex_h, tex_layers, seeds, samples, fast, features, row0, row1, nthreads, out, counters);
+}
+
+int oracle_trace2(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,
+                  const void* camera, const uint8_t* const* tex, const int32_t* tex_w, const int32_t* tex_h,
+                  const int32_t* tex_layers, const double* seeds, int samples, int precision, int rng_mode, int row0, int row1,
+                  int nthreads, double* out, uint64_t* counters) {
+    return oracle_trace3(objects, n_objects, triangles, n_triangles, groups, n_groups, camera, tex, tex_w, tex_h, tex_layers, seeds,
+                         samples, precision, rng_mode, 0, row0, row1, nthreads, out, counters);
 }
 
 int oracle_trace(const void* objects, int n_objects, const void* triangles, int n_triangles, const void* groups, int n_groups,

@@ -98,6 +98,8 @@ __device__ __forceinline__ void m_sincos_2pi(float a, float* s, float* c) {
     *s = -sa; *c = -ca;
 }
 __device__ __forceinline__ void m_sincos_2pi(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ void m_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void m_sincos(double a, double* s, double* c) { sincos(a, s, c); }
 __device__ __forceinline__ float m_acos(float a) { return acosf(a); }
 __device__ __forceinline__ double m_acos(double a) { return acos(a); }
 __device__ __forceinline__ float m_atan2(float a, float b) { return atan2f(a, b); }
@@ -174,6 +176,10 @@ template <typename R> struct DCam {
 
 struct DTex { const uchar4* data; int w, h, layers; };
 
+// Next-event estimation (tracer.cl:786-825) samples every object whose emission.x > 0 as a sphere around the
+// translation of its `transform`, scaled by the largest diagonal entry; transform[0] enters the attenuation.
+template <typename R> struct alignas(16) DLight { R ox, oy, oz, scale, t0, er, eg, eb; int obj, pad[3]; };
+
 // Per mesh (group) object: what the rebuilt BVH needs besides the object's hot record.
 template <typename R> struct alignas(16) DMesh {
     R root_lo[3], root_hi[3];   // padded extent of the object's triangles: conservative pre-cull
@@ -223,6 +229,8 @@ template <typename R> struct Params {
     double4* acc;               // progressive rendering: running per-pixel sums (local rows), or NULL
     int out_f32;
     int nee, caps;              // optional features the reference ships disabled (tracer.cl:1168, :437-444); 0 = upstream behaviour
+    DLight<R> light[kMaxObjects];   // next-event estimation: the emissive objects, scene order
+    int n_lights;
     int rows;                   // local rows rendered by this device
     int samples;                // total samples per pixel (enters the RNG seeding and the final weight)
     int sample_begin, sample_end;   // samples rendered by this launch: [begin, end) (0, samples for a full render)
@@ -690,7 +698,7 @@ __device__ __forceinline__ void run_spheres(const Params<R>& P, int n, V3<R> ro,
 
 // One analytic object of the slow loop against one ray (`type` is warp-uniform).
 template <typename R>
-__device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int type, V3<R> ro, V3<R> rd, R eps, Hit<R>& h) {
+__device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int type, V3<R> ro, V3<R> rd, R eps, bool caps, Hit<R>& h) {
     if (type == 0) {                                             // plane, tracer.cl:478-483
         R oy = ob.inv[4] * ro.x + ob.inv[5] * ro.y + ob.inv[6] * ro.z + ob.inv[7];
         R dy = ob.inv[4] * rd.x + ob.inv[5] * rd.y + ob.inv[6] * rd.z;
@@ -720,6 +728,12 @@ __device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int typ
                 R y0 = o.y + t0 * d.y, y1 = o.y + t1 * d.y;
                 if (y0 > ob.aux[0] && y0 < ob.aux[1]) offer_ordered(h, t0, j, eps);
                 if (y1 > ob.aux[0] && y1 < ob.aux[1]) offer_ordered(h, t1, j, eps);
+                if (caps && !(m_abs(d.y) < eps)) {                  // end caps, tracer.cl:282-310 (upstream: disabled at :437-444)
+                    const R tc0 = m_div(ob.aux[0] - o.y, d.y), tc1 = m_div(ob.aux[1] - o.y, d.y);
+                    const R x0 = o.x + tc0 * d.x, z0 = o.z + tc0 * d.z, x1 = o.x + tc1 * d.x, z1 = o.z + tc1 * d.z;
+                    if (x0 * x0 + z0 * z0 <= R(1) && tc0 > R(0)) offer_ordered(h, tc0, j, eps);
+                    if (x1 * x1 + z1 * z1 <= R(1) && tc1 > R(0)) offer_ordered(h, tc1, j, eps);
+                }
             }
         }
     } else if (type == 3) {                                      // cube, tracer.cl:378-394
@@ -745,7 +759,7 @@ __device__ __forceinline__ void closest_analytic(const Params<R>& P, V3<R> ro, V
     if (h.obj >= 0) h.obj = P.fast_obj[h.obj];                   // slot -> object index
     for (int k = 0; k < P.n_slow; ++k) {
         const int j = P.slow_obj[k], kind = P.slow_kind[k];
-        if (kind == 3) test_object<R>(P.hot[j], j, P.hot[j].type, ro, rd, eps, h);
+        if (kind == 3) test_object<R>(P.hot[j], j, P.hot[j].type, ro, rd, eps, P.caps != 0, h);
         else if (kind == 0) {                                    // a plane beyond the unrolled slots: same arithmetic as there
             R dy;
             const R t = plane_t(P.slow_rec[k], ro, rd, dy);
@@ -789,8 +803,11 @@ __device__ __forceinline__ void camera_ray(const Params<R>& P, R px, R py, float
 
 // One surface interaction: normal, material branch, next ray, fused mask/accumulate (tracer.cl:895-1107,
 // 1116-1176).  Returns true when the path ends here.
-template <typename R, int RNG>
-__device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, Path<R>& s, float fgi) {
+// What next-event estimation needs from a shaded bounce (the reference's stored `bounce`, tracer.cl:72-80).
+template <typename R> struct NeeInfo { V3<R> point, normal, color, mask; unsigned b; bool on; };
+
+template <typename R, int RNG, bool NEE>
+__device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, Path<R>& s, float fgi, NeeInfo<R>& ni) {
     const R eps = P.eps, pi = P.pi;
     V3<R>& ro = s.ro; V3<R>& rd = s.rd;
     const unsigned n = s.n;
@@ -909,6 +926,10 @@ __device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, P
 
     // fused shading, tracer.cl:1116-1176: refraction bounces are skipped; an emitter adds
     // mask*emission (or, when hit directly by the camera ray, replaces accum by its colour)
+    if (NEE) {          // tracer.cl:1168 runs for every stored bounce that is neither a refraction nor an emitter, with the mask BEFORE this bounce
+        ni.on = !(entering || exiting) && !(emis.x > R(0));
+        ni.point = position; ni.normal = nv; ni.color = colr; ni.mask = s.mask; ni.b = s.b;
+    }
     if (!(entering || exiting)) {
         s.accum = s.accum + s.mask * emis;
         if (emis.x > R(0)) { if (s.b == 0) s.accum = colr; }
@@ -958,8 +979,9 @@ template <typename R> __device__ __forceinline__ PixelSlot pixel_slot(const Para
 // ---- the kernel ----------------------------------------------------------------------------------
 // GROUPS = the scene contains mesh objects: only then is the cooperative BVH walk (and its shared-memory
 // stacks) compiled in.
-template <typename R, int RNG, bool GROUPS>
-__global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS_F64) : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
+// NEE = next-event estimation compiled in (the reference ships it commented out; ptc_job.features enables it).
+template <typename R, int RNG, bool GROUPS, bool NEE = false>
+__global__ void __launch_bounds__(kBlockThreads, NEE ? (sizeof(R) == 8 ? 2 : 4) : (sizeof(R) == 8 ? (GROUPS ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS_F64) : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
     extern __shared__ int2 mesh_stacks[];       // GROUPS: one stack of P.stack_entries per 8-lane group (sized by the host from the scene's BVH)
     const unsigned cluster_size = cluster_nctarank(), cluster_rank = cluster_ctarank();
     const PixelSlot px = pixel_slot(P, cluster_rank, cluster_size);
@@ -1025,7 +1047,41 @@ __global__ void __launch_bounds__(kBlockThreads, (sizeof(R) == 8 ? (GROUPS ? PTK
         if (GROUPS) closest_mesh<R>(P, s.ro, s.rd, live, lane, h, stack_base);
 
         bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
-        if (live && h.obj >= 0) done = shade_hit<R, RNG>(P, h, s, fgi);
+        NeeInfo<R> ni;
+        ni.on = false;
+        if (live && h.obj >= 0) done = shade_hit<R, RNG, NEE>(P, h, s, fgi, ni);
+        if constexpr (NEE) {
+            // Next-event estimation, tracer.cl:786-825: one shadow ray per light towards a point of the light's bounding
+            // sphere, for every lane whose bounce takes part; the shadow rays of a warp are traced together.
+            ni.on = ni.on && live && h.obj >= 0;
+            for (int q = 0; q < P.n_lights; ++q) {
+                const DLight<R>& L = P.light[q];
+                const unsigned l = (unsigned)L.obj;
+                const R nd = R(s.n);
+                const float r1 = noise3d<RNG>(fgi, (float)(nd + R(ni.b * l)), fgi2);
+                const float r2 = noise3d<RNG>(fgi, fgi2, (float)(nd + R(ni.b * ni.b * l)));
+                const R lat = m_acos(R(2) * R(r1) - R(1)) - P.pi * R(2);        // randomPointOnSphere, tracer.cl:321-336, as written
+                const R lon = R(2) * P.pi * R(r2);
+                R slat, clat, slon, clon;
+                m_sincos(lat, &slat, &clat); m_sincos(lon, &slon, &clon);
+                const V3<R> lp = {L.ox + clat * clon * L.scale, L.oy + (slat - P.pi * R(0.25)) * L.scale, L.oz + clat * slon * L.scale};
+                const V3<R> to = lp - ni.point;
+                const V3<R> dir = to * m_div(R(1), m_sqrt(dot(to, to)));
+                const V3<R> so = ni.point + dir * P.eps;
+                const R ldn = dot(dir, ni.normal);
+                const bool test = ni.on && ldn > R(0);
+                if (__any_sync(kFullMask, test)) {
+                    Hit<R> hs;
+                    closest_analytic<R>(P, so, dir, hs);
+                    if (GROUPS) closest_mesh<R>(P, so, dir, test, lane, hs, stack_base);
+                    if (test && hs.obj == (int)l && hs.t > P.eps) {
+                        const R att = R(1) - m_div(hs.t, m_sqrt(hs.t * hs.t + L.t0 * L.t0));
+                        const V3<R> emis = {L.er, L.eg, L.eb};
+                        s.accum = s.accum + ((ni.color * emis) * ldn) * ni.mask * att;
+                    }
+                }
+            }
+        }
         if (done) {
             col_sum[0][threadIdx.x] += (double)s.accum.x; col_sum[1][threadIdx.x] += (double)s.accum.y;   // tracer.cl:1179
             col_sum[2][threadIdx.x] += (double)s.accum.z;

@@ -64,6 +64,8 @@ template <typename R> struct HostScene {
     ptk::DFast<R> slow_rec[ptk::kMaxObjects], slow_rec2[ptk::kMaxObjects];
     int mesh_obj[ptk::kMaxObjects], n_mesh = 0;
     int stack_need = 0;        // deepest deferred-child stack any mesh of the scene can need
+    ptk::DLight<R> light[ptk::kMaxObjects];
+    int n_lights = 0;
     std::vector<ptk::DObjShade<R>> shade;
     std::vector<ptk::DMesh<R>> mesh;              // one per object
     std::vector<R> lens;       // sunflower lens points, 2 per sample (empty without depth of field)
@@ -443,6 +445,19 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
         out.mesh.push_back(m);
         out.shade.push_back(o);
     }
+    // lights of the next-event estimation (tracer.cl:786-792): every object with emission.x > 0
+    out.n_lights = 0;
+    std::memset(out.light, 0, sizeof out.light);
+    for (int i = 0; i < job.n_objects; ++i) {
+        const ptw_object& s = objs[i];
+        if (!(s.emission[0] > 0.0)) continue;
+        ptk::DLight<R>& L = out.light[out.n_lights++];
+        L.ox = R(s.transform[3]); L.oy = R(s.transform[7]); L.oz = R(s.transform[11]);
+        L.scale = R(std::fmax(std::fmax(s.transform[0], s.transform[5]), s.transform[10]));
+        L.t0 = R(s.transform[0]);
+        L.er = R(s.emission[0]); L.eg = R(s.emission[1]); L.eb = R(s.emission[2]);
+        L.obj = i;
+    }
     // Intersection order.  Planes and spheres whose `inverse` is a similarity (uniform scale, any rotation: the unit
     // sphere is then a world-space sphere of radius 1/s around the transform's translation) take the kernel's unrolled
     // fast slots -- three runs "spheres, planes, spheres" filled greedily in scene order, so fast objects keep their
@@ -708,6 +723,8 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     P.pi = R(double(3.14159265359f));
     P.eps = R(0.0001);
     P.nee = c.nee; P.caps = c.caps;
+    std::memcpy(P.light, s.light, sizeof P.light);
+    P.n_lights = s.n_lights;
     // where the pixels go: an attached frame (by frame row), the context's gather buffer on dev[0] (by position among
     // the context's rows), or this device's own packed rows
     if (c.frame) { P.out = c.frame->data; P.out_row = d.row_map; P.out_f32 = c.frame->format == PTC_FRAME_F32; }
@@ -752,7 +769,10 @@ template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScen
     dim3 grid((unsigned)((tiles + tiles_per_block - 1) / tiles_per_block * d.cluster), 1, 1);
     dim3 block(ptk::kBlockThreads, 1, 1);
     const size_t smem = meshes ? size_t(ptk::kBlockThreads / ptk::kWide) * size_t(P.stack_entries) * sizeof(int2) : 0;
-    if (meshes) {
+    if (c.nee) {                  // the next-event-estimation kernels (parity RNG stream only, checked in open_impl)
+        if (meshes) launch_kernel(ptk::trace_kernel<R, ptk::RNG_PARITY, true, true>, grid, block, smem, d.cluster, d.stream, P);
+        else launch_kernel(ptk::trace_kernel<R, ptk::RNG_PARITY, false, true>, grid, block, smem, d.cluster, d.stream, P);
+    } else if (meshes) {
         if (fast) launch_kernel(ptk::trace_kernel<R, ptk::RNG_FAST, true>, grid, block, smem, d.cluster, d.stream, P);
         else launch_kernel(ptk::trace_kernel<R, ptk::RNG_PARITY, true>, grid, block, smem, d.cluster, d.stream, P);
     } else {
@@ -804,15 +824,21 @@ void destroy(ptc_context* c) {
 }
 
 // Sample slices per pixel for a device that owns `px` pixels.  Small frames cannot fill 148 SMs with one thread
-// per pixel, and blocks that live for the whole frame leave a long tail (measured on B200: a 1/8-frame shard ran
-// 36.3 ms with 1 slice, 29.3 ms with 32), so each pixel's samples are split into interleaved slices until there are
-// ~16x the resident thread capacity in total threads; scenes with meshes, whose pixels differ several-fold in cost,
-// get 2x finer slices (round 2, whole frame on one B200, teapot / gopher Gpaths/s at 1, 2, 4, 8, 16, 32 slices:
-// 2.30 / 1.75, 3.12 / 2.22, 3.54 / 2.58, 3.67 / 2.62, 3.50 / 2.49, 3.44 / 2.45).  A power of two, at most
-// kBlockWarps * kMaxCluster = 32: all slices of a pixel sit in one thread-block cluster, which reduces them.
+// per pixel, and blocks that live for the whole frame leave a long tail, so each pixel's samples are split into
+// interleaved slices; all slices of a pixel sit in one thread-block cluster (kBlockWarps per block), which reduces
+// them, so the count is a power of two <= kBlockWarps * kMaxCluster = 32.  Measured on one B200 (round 2, Gpaths/s):
+//   whole 1280x960 frame, slices 1 / 2 / 4 / 8 / 16 / 32: reference scene 12.72 / 12.89 / 12.96 / 12.99 / 12.42 / 12.36,
+//                                                          teapot 2.30 / 3.12 / 3.54 / 3.67 / 3.50 / 3.44;
+//   one 1/8 shard of it (the 8-GPU case), 4 / 8 / 16 / 32:  reference scene 24.3 / 23.8 / 24.5 / 24.5 ms,
+//                                                          teapot 154 / 106 / 89 / 83 ms.
+// Clusters above two blocks cost a few per cent (eight blocks have to become free in one GPC together), so analytic
+// scenes stay at 8 slices unless the frame is too small to fill the machine; scenes with meshes, whose pixels differ
+// several-fold in cost, want ~10 M threads in total.
 int plan_slices(long long px, int sm_count, bool meshes, int samples) {
-    const long long want = (long long)sm_count * 2048 * (meshes ? 32 : 16);
-    long long sl = px ? (want + px - 1) / px : 1;
+    const long long resident = (long long)sm_count * 1024;                        // threads at 8 blocks x 128 per SM
+    long long sl;
+    if (meshes) sl = std::max<long long>(8, px ? ((long long)sm_count * 2048 * 32 + px - 1) / px : 1);
+    else sl = px * 8 >= 2 * resident ? 8 : (px ? (4 * resident + px - 1) / px : 1);
     if (const char* ov = std::getenv("PTC_SLICES")) sl = std::atoll(ov);    // tuning override
     const long long cap = std::min<long long>(samples, ptk::kBlockWarps * ptk::kMaxCluster);
     if (sl > cap) sl = cap;
@@ -835,6 +861,7 @@ ptc_context* open_impl(const ptc_job& job) {
     c.width = cam->width; c.height = cam->height; c.samples = job.samples;
     c.precision = job.precision; c.rng_mode = job.rng_mode; c.n_objects = job.n_objects;
     c.nee = (job.features & PTC_FEATURE_NEE) ? 1 : 0;
+    if (c.nee && job.rng_mode != PTC_RNG_PARITY) fail("PTC_FEATURE_NEE is available with PTC_RNG_PARITY only");
     c.caps = (job.features & PTC_FEATURE_CYLINDER_CAPS) ? 1 : 0;
     c.shard_count = job.shard_count > 1 ? job.shard_count : 1;
     c.shard_index = job.shard_count > 1 ? job.shard_index : 0;
