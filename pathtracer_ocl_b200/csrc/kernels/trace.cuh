@@ -197,7 +197,7 @@ template <typename R> struct Params {
     DFast<R> fast2[kFastSlots]; // sphere slots of kind 1: the diagonal of `inverse`
     int fast_kind[kFastSlots];  // sphere slots: 0 = similarity, 1 = axis-aligned ellipsoid
     int fast_n[4];              // objects in run A, B, C
-    int fast_obj[kFastSlots];   // slot -> object index
+    int fast_obj[kFastSlots + 1];   // slot -> object index; entry kFastSlots ("no slot hit") maps to -1
     DObjHot<R> hot[kMaxObjects];    // read by the slow loop and the mesh walk only
     int slow_obj[kMaxObjects];  int n_slow;    // analytic objects outside the fast slots (general spheres, cylinders, cubes, overflow), scene order
     int slow_kind[kMaxObjects];                // 3: by its hot record; 0 plane / 1 similarity sphere / 2 ellipsoid: by slow_rec, with the slots' arithmetic
@@ -267,6 +267,8 @@ __device__ __forceinline__ float3 sample_rgba8(const DTex& t, float s, float tt,
     // UNORM8 -> float is c / 255.0f correctly rounded.  One multiply by 1/255 plus one residual step
     // (e = c - q*255 exactly by FMA; q += e/255) gives that quotient bit for bit for all 256 inputs
     // (checked exhaustively in tests/test_oracle_golden.py) at 3 instructions instead of an IEEE divide.
+    // (Measured and rejected: replacing the byte -> float conversion (I2F, XU pipe) by a byte permute into the mantissa
+    // of 2^23 minus 2^23: two instructions for one, -7 % on the environment-map scene, -9 % on the textures scene.)
     auto unorm8 = [](unsigned char p) {
         const float c = (float)p, r = 0x1.010102p-8f;           // float(1/255)
         const float q = __fmul_rn(c, r);
@@ -751,12 +753,12 @@ __device__ __forceinline__ void test_object(const DObjHot<R>& ob, int j, int typ
 template <typename R>
 __device__ __forceinline__ void closest_analytic(const Params<R>& P, V3<R> ro, V3<R> rd, Hit<R>& h) {
     const R eps = P.eps;
-    h.t = R(1024); h.obj = -1; h.tri = -1; h.u = R(0); h.v = R(0);
+    h.t = R(1024); h.obj = kFastSlots; h.tri = -1; h.u = R(0); h.v = R(0);
     const R a = m_fma(rd.x, rd.x, m_fma(rd.y, rd.y, rd.z * rd.z)), inv_a = m_rcp(a);
     run_spheres<R, 0, 0, kFastA>(P, P.fast_n[0], ro, rd, a, inv_a, eps, h);
     run_planes<R, kFastA, kFastA + kFastB>(P, P.fast_n[1], ro, rd, eps, h);
     run_spheres<R, kFastA + kFastB, kFastA + kFastB, kFastSlots>(P, P.fast_n[2], ro, rd, a, inv_a, eps, h);
-    if (h.obj >= 0) h.obj = P.fast_obj[h.obj];                   // slot -> object index
+    h.obj = P.fast_obj[h.obj];                                   // slot -> object index (kFastSlots -> -1: nothing hit yet)
     for (int k = 0; k < P.n_slow; ++k) {
         const int j = P.slow_obj[k], kind = P.slow_kind[k];
         if (kind == 3) test_object<R>(P.hot[j], j, P.hot[j].type, ro, rd, eps, P.caps != 0, h);
@@ -904,21 +906,25 @@ __device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, P
         colr = {ob.color[0], ob.color[1], ob.color[2]};
         emis = {ob.emission[0], ob.emission[1], ob.emission[2]};
         if (ob.flags & 1) {
-            if (type == 0) {
-                float3 c = sample_rgba8(P.tex[0], (float)(lp.x * ob.tex_sx), (float)(lp.z * ob.tex_sy), ob.tex_index);
-                colr = {R(c.x), R(c.y), R(c.z)};
-            } else if (type == 1) {                                           // sphericalMap, tracer.cl:178-213
+            // texture coordinates per shape, then ONE bilinear fetch (a single inlined copy of the exact filter: the
+            // kernel's code size is what the textured scenes stall on)
+            float tu = 0.f, tv = 0.f;
+            int cls = -1;
+            if (type == 0) { tu = (float)(lp.x * ob.tex_sx); tv = (float)(lp.z * ob.tex_sy); cls = 0; }
+            else if (type == 1) {                                             // sphericalMap, tracer.cl:178-213
                 R theta = m_atan2(lp.x, lp.z);
                 R radius = sqrt(dot(lp, lp));
                 R phi = m_acos(lp.y / radius);
                 R su = R(1) - (theta / (R(2) * pi) + R(0.5));
                 R sv = R(1) - phi / pi;
-                float3 c = sample_rgba8(P.tex[1], (float)su, (float)(R(1) - sv), ob.tex_index);
-                colr = {R(c.x), R(c.y), R(c.z)};
+                tu = (float)su; tv = (float)(R(1) - sv); cls = 1;
             } else if (type == 3) {
                 R cu, cv;
                 cube_uv(lp, cu, cv);
-                float3 c = sample_rgba8(P.tex[2], (float)cu, (float)cv, ob.tex_index);
+                tu = (float)cu; tv = (float)cv; cls = 2;
+            }
+            if (cls >= 0) {
+                float3 c = sample_rgba8(P.tex[cls], tu, tv, ob.tex_index);
                 colr = {R(c.x), R(c.y), R(c.z)};
             }
         }

@@ -59,7 +59,7 @@ template <typename R> struct HostScene {
     ptk::DObjHot<R> hot[ptk::kMaxObjects];
     ptk::DFast<R> fast[ptk::kFastSlots];
     ptk::DFast<R> fast2[ptk::kFastSlots];
-    int fast_n[4], fast_obj[ptk::kFastSlots], fast_kind[ptk::kFastSlots];
+    int fast_n[4], fast_obj[ptk::kFastSlots + 1], fast_kind[ptk::kFastSlots];
     int slow_obj[ptk::kMaxObjects], slow_kind[ptk::kMaxObjects], n_slow = 0;
     ptk::DFast<R> slow_rec[ptk::kMaxObjects], slow_rec2[ptk::kMaxObjects];
     int mesh_obj[ptk::kMaxObjects], n_mesh = 0;
@@ -465,6 +465,7 @@ template <typename R> void flatten(const ptc_job& job, HostScene<R>& out) {
     out.n_slow = out.n_mesh = 0;
     std::memset(out.slow_kind, 0, sizeof out.slow_kind); std::memset(out.slow_rec, 0, sizeof out.slow_rec); std::memset(out.slow_rec2, 0, sizeof out.slow_rec2);
     for (int k = 0; k < 4; ++k) out.fast_n[k] = 0;
+    out.fast_obj[ptk::kFastSlots] = -1;
     for (int k = 0; k < ptk::kFastSlots; ++k) {
         out.fast_obj[k] = -1; out.fast_kind[k] = 0;
         out.fast[k] = out.fast2[k] = ptk::DFast<R>{R(0), R(0), R(0), R(0)};
