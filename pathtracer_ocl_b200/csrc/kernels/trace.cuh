@@ -237,6 +237,7 @@ template <typename R> struct Params {
     int slices;                 // sample slices per pixel: a power of two <= kBlockWarps * cluster size
     int slices_per_block;       // min(slices, kBlockWarps): the warps of a block are slices_per_block slices of
                                 // kBlockWarps / slices_per_block tiles; a cluster holds all slices of its tiles
+    int lane_walk_min;          // mesh walk: rays per warp from which every lane walks its own ray (mesh_hit_lanes); 33 = never
     int stack_entries;          // mesh walk: entries of one 8-lane group's stack in dynamic shared memory (scene's worst case + 1)
     R pi;                       // (double)3.14159265359f, tracer.cl:1
     R eps;                      // 0.0001, tracer.cl:4
@@ -489,6 +490,9 @@ __device__ __forceinline__ int2 stack_load(unsigned addr) {
     int2 e; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr) : "memory"); return e;
 }
 
+#ifdef PTK_HIST
+__device__ unsigned long long ptk_hist[40];      // tuning build only: histogram of rays per warp that enter a mesh walk
+#endif
 // One mesh object against the rays of the lanes with `want` set.  Called by all 32 lanes.  `ro`, `rd`:
 // this lane's ray in world space.  `stk`: shared-window address of this lane's GROUP's stack.
 //
@@ -508,6 +512,9 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& o
     constexpr int kDone = 0x7fffffff;
     constexpr unsigned kNoKey = 0xffffffffu;
     unsigned todo = __ballot_sync(kFullMask, want);
+#ifdef PTK_HIST
+    if (lane == 0) atomicAdd(&ptk_hist[__popc(todo)], 1ull);
+#endif
     while (todo) {                                                    // a round: up to four rays, one per group
         // owners of this round: the four lowest set bits of `todo`
         const unsigned t1 = todo & (todo - 1), t2 = t1 & (t1 - 1), t3 = t2 & (t2 - 1);
@@ -606,6 +613,83 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& o
     }
 }
 
+// The same walk with ONE LANE PER RAY, for warps where many lanes reach the mesh at once (camera rays of a tile that
+// looks at the mesh, a mirror in front of it).  Measured on B200 (histogram of rays per warp entering mesh_hit):
+// cooperative rounds hold four rays, so a warp with 32 wanting lanes pays eight rounds -- 27 % (teapot), 42 % (gopher),
+// 97 % (cube-map scene) of all rounds came from warps with nine or more rays.  Here every lane tests the (up to) eight
+// children of its node itself, visits the nearest first and keeps the others on a private stack in local memory; leaves
+// test their triangles one after the other with the same acceptance rule (closest t, then lowest rank, reference node
+// chain).  No shuffles, no ballots; lanes diverge freely.  `o`, `d`: this lane's ray in the OBJECT's space.
+// Threshold, measured (teapot / gopher / cube-map scene, Gpaths/s, at 8, 16, 24, 32 rays and "never"): 4.01 / 2.65 / 9.95,
+// 4.13 / 2.84 / 9.91, 4.24 / 2.92 / 9.97, 4.26 / 2.94 / 9.71, 4.26 / 2.95 / 8.00 -- divergence and the local-memory
+// stacks make the private walk pay only when (nearly) the whole warp wants the mesh.
+constexpr int kLaneWalkMin = 30;
+template <typename R>
+__device__ __forceinline__ void mesh_hit_lanes(const Params<R>& P, const DMesh<R>& m, int j, V3<R> o, V3<R> d, const Slab<R>& s, Hit<R>& h) {
+    const R eps = P.eps;
+    constexpr int kDone = 0x7fffffff;
+    const IDir<R> k = inv_dir(d);
+    const bool whole_chain = !(m.flags & 1) || !(s.dx && s.dy && s.dz);
+    R ct = h.t;
+    int crank = h.obj > j ? 0x7fffffff : -1;      // equal t: an earlier object keeps the hit, a later one loses it to this mesh
+    int cslot = -1;
+    R cu = R(0), cv = R(0);
+    int2 stk[kWideStack];
+    int sp = 0, cur = m.bvh_root;
+    while (cur != kDone) {
+        int next = kDone;
+        if (cur >= 0) {                                               // inner node: its children are packed at the front
+            const R limit = ct * R(1.0001);
+            int next_key = 0x7fffffff;
+            for (int c = 0; c < kWide; ++c) {
+                const V4<R> a = ldg4(&P.wide[(cur * kWide + c) * 2]), b = ldg4(&P.wide[(cur * kWide + c) * 2 + 1]);
+                const int code = child_code(a.w);
+                if (code == kEmptyChild) break;
+                R tn;
+                if (!keep_box(o, k, a.x, b.x, a.y, b.y, a.z, b.z, limit, tn)) continue;
+                const int key = stack_key(tn) & 0x7fffffff;           // float bits of a lower bound of tn (tn >= 0)
+                if (key < next_key) {                                 // nearer than the nearest so far: that one is deferred
+                    if (next != kDone) stk[sp++] = make_int2(next, next_key);
+                    next = code; next_key = key;
+                } else stk[sp++] = make_int2(code, key);
+            }
+        } else {                                                      // leaf: its triangles in turn, Moeller-Trumbore (tracer.cl:640-675)
+            const int lc = ~cur, count = lc & 15, first = lc >> 4;
+            for (int i = 0; i < count; ++i) {
+                const int slot = first + i;
+                const V4<R> q0 = ldg4(&P.tri_test[3 * slot]), q1 = ldg4(&P.tri_test[3 * slot + 1]);
+                const V3<R> e2 = {q1.z, q1.w, ldg1(&P.tri_test[3 * slot + 2].x)};
+                const V3<R> e1 = {q0.w, q1.x, q1.y};
+                const V3<R> dxe2 = cross(d, e2);
+                const R det = dot(e1, dxe2);
+                if (m_abs(det) < eps) continue;
+                const R f = m_rcp(det);
+                const V3<R> sv = {o.x - q0.x, o.y - q0.y, o.z - q0.z};
+                const R u = f * dot(sv, dxe2);
+                if (u < R(0) || u > R(1)) continue;
+                const V3<R> sxe1 = cross(sv, e1);
+                const R v = f * dot(d, sxe1);
+                if (v < R(0) || (u + v) > R(1)) continue;
+                const R t = f * dot(e2, sxe1);
+                if (!(t > eps && t <= ct)) continue;
+                const int2 info = __ldg(&P.tri_info[slot]);           // (rank in the reference's recording order, reference node)
+                if ((t < ct || info.x < crank) && reference_tests_node(P, o, d, s, info.y, whole_chain)) {
+                    ct = t; crank = info.x; cslot = slot; cu = u; cv = v;
+                }
+            }
+        }
+        if (next == kDone) {                                          // pop; children beyond the current best are dropped
+            const R lim2 = ct * R(1.0001);
+            while (sp > 0) {
+                const int2 e = stk[--sp];
+                if (!(R(__int_as_float(e.y)) > lim2)) { next = e.x; break; }
+            }
+        }
+        cur = next;
+    }
+    if (cslot >= 0) { h.t = ct; h.obj = j; h.tri = cslot; h.u = cu; h.v = cv; }
+}
+
 // All mesh objects of the scene (tracer.cl:598-720), after the analytic objects.  Called by all 32 lanes.
 template <typename R>
 __device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h, unsigned stk) {
@@ -622,7 +706,13 @@ __device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R>
             const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);
             const bool want = live && finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1) &&
                               keep_box(o, inv_dir(d), m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], h.t * R(1.0001), tn);
-            mesh_hit<R>(P, ob, m, j, ro, rd, want, lane, h, stk);
+            // (fp32 only: in double the private stacks and the second walk cost the kernel more registers than they save time)
+            if (sizeof(R) == 4 && __popc(__ballot_sync(kFullMask, want)) >= P.lane_walk_min) {
+                if (want) mesh_hit_lanes<R>(P, m, j, o, d, s, h);
+                __syncwarp();
+            } else {
+                mesh_hit<R>(P, ob, m, j, ro, rd, want, lane, h, stk);
+            }
         }
     }
 }
@@ -906,8 +996,9 @@ __device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, P
         colr = {ob.color[0], ob.color[1], ob.color[2]};
         emis = {ob.emission[0], ob.emission[1], ob.emission[2]};
         if (ob.flags & 1) {
-            // texture coordinates per shape, then ONE bilinear fetch (a single inlined copy of the exact filter: the
-            // kernel's code size is what the textured scenes stall on)
+            // texture coordinates per shape, then ONE bilinear fetch: a single inlined copy of the exact filter -- the
+            // kernel's code size is what the textured scenes stall on (+27 % on the textures scene).  The fp64 kernels keep
+            // a fetch per shape: merged, their register allocation came out worse (-7 % .. -17 % on scenes without textures).
             float tu = 0.f, tv = 0.f;
             int cls = -1;
             if (type == 0) { tu = (float)(lp.x * ob.tex_sx); tv = (float)(lp.z * ob.tex_sy); cls = 0; }
@@ -923,8 +1014,19 @@ __device__ __forceinline__ bool shade_hit(const Params<R>& P, const Hit<R>& h, P
                 cube_uv(lp, cu, cv);
                 tu = (float)cu; tv = (float)cv; cls = 2;
             }
-            if (cls >= 0) {
-                float3 c = sample_rgba8(P.tex[cls], tu, tv, ob.tex_index);
+            if (sizeof(R) == 4) {
+                if (cls >= 0) {
+                    float3 c = sample_rgba8(P.tex[cls], tu, tv, ob.tex_index);
+                    colr = {R(c.x), R(c.y), R(c.z)};
+                }
+            } else if (cls == 0) {
+                float3 c = sample_rgba8(P.tex[0], tu, tv, ob.tex_index);
+                colr = {R(c.x), R(c.y), R(c.z)};
+            } else if (cls == 1) {
+                float3 c = sample_rgba8(P.tex[1], tu, tv, ob.tex_index);
+                colr = {R(c.x), R(c.y), R(c.z)};
+            } else if (cls == 2) {
+                float3 c = sample_rgba8(P.tex[2], tu, tv, ob.tex_index);
                 colr = {R(c.x), R(c.y), R(c.z)};
             }
         }

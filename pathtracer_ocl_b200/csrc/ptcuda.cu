@@ -701,6 +701,8 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     std::memcpy(P.mesh_obj, s.mesh_obj, sizeof P.mesh_obj);
     P.n_slow = s.n_slow; P.n_mesh = s.n_mesh;
     P.stack_entries = (s.stack_need + 1) | 1;          // odd: the four groups of a warp push to different banks
+    P.lane_walk_min = ptk::kLaneWalkMin;
+    if (const char* ov = std::getenv("PTC_LANE_WALK_MIN")) P.lane_walk_min = std::atoi(ov);      // tuning override
     P.shade = static_cast<const ptk::DObjShade<R>*>(d.shade);
     P.lens = static_cast<const R*>(d.lens);
     P.n_objects = c.n_objects;
@@ -1407,6 +1409,15 @@ int ptc_debug_fma_peak(int device, double* tflops, char* err, int errlen) {
         *tflops = 2.0 * 8 * 16 * double(iters) * blocks * threads / (best * 1e-3) / 1e12;
     });
 }
+
+#ifdef PTK_HIST
+int ptc_debug_hist(unsigned long long* out40, int reset) {
+    cudaDeviceSynchronize();
+    if (out40) cudaMemcpyFromSymbol(out40, ptk::ptk_hist, 40 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[40] = {}; cudaMemcpyToSymbol(ptk::ptk_hist, z, sizeof z); }
+    return 0;
+}
+#endif
 
 // The FP64 twin: achieved DFMA throughput in TFLOP/s (the roofline of the fp64 mode).
 int ptc_debug_dfma_peak(int device, double* tflops, char* err, int errlen) {

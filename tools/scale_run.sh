@@ -1,20 +1,30 @@
 #!/bin/bash
-# Strong-scaling run of bench.py on 1/2/4/8 GPUs of one box (whatever the box has).
+# Strong-scaling curves from ONE multi-GPU lease: bench.py for every BASELINE config at the GPU counts the box has.
+#   tools/scale_run.sh [configs...]      default: 2 3 4 5 5e 5c     env: NS="2 4 8" (N = 1 comes from the single-GPU runs)
+# Writes gpurun_out/scale_cfg<config>_n<N>.json (one bench line each).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
-python bench.py --gpus 1 --steps 5 --warmup 3 | tee gpurun_out/scale_1.json | cut -c1-300
-for n in 2 4 8; do
-  if [ "$n" -le "$NG" ]; then
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 5 --warmup 3 2>/dev/null | grep '^{' | tee gpurun_out/scale_$n.json | cut -c1-300
-  fi
-done
-[ -n "$SCALE_ONLY" ] && exit 0
-# BASELINE config 5 family (3840x2160, 4096 spp) on all GPUs: textured planes/spheres, env sphere, env cube + mesh
-for sc in textures envmap cubemap; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus $NG --steps 2 --warmup 3 --scene $sc --width 3840 --height 2160 --samples 4096 --aperture 0 --focal-length 0 --no-cpu-baseline 2>/dev/null | grep '^{' | tee gpurun_out/cfg5_${sc}_$NG.json | cut -c1-300
-done
-# BASELINE configs 3 and 4 (mesh scenes, full 2048 spp) on all GPUs
-for sc in teapot gopher; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus $NG --steps 3 --warmup 3 --scene $sc --aperture 0 --focal-length 0 --no-cpu-baseline 2>/dev/null | grep '^{' | tee gpurun_out/${sc}_$NG.json | cut -c1-300
+CONFIGS=${@:-2 3 4 5 5e 5c}
+NS=${NS:-2 4 8}
+port=29500
+for cfg in $CONFIGS; do
+  for n in $NS; do
+    [ "$n" -le "$NG" ] || continue
+    port=$((port+1))
+    if [ "$n" -eq 1 ]; then
+      python bench.py --config $cfg --steps 3 --warmup 3 --no-cpu-baseline --no-extras 2>/dev/null | grep '^{' > gpurun_out/scale_cfg${cfg}_n$n.json
+    else
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --config $cfg --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/scale_err.log | grep '^{' > gpurun_out/scale_cfg${cfg}_n$n.json
+    fi
+    python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/scale_cfg${cfg}_n$n.json"))
+    sp = d.get("single_process_multi_gpu", {})
+    print("cfg$cfg N=$n value %.0f e2e %.0f ms %.2f kernel_ms %.2f frac %s one-process identical=%s" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], sp.get("bit_identical_to_gathered")))
+except Exception as e:
+    print("cfg$cfg N=$n FAILED", e); print(open("gpurun_out/scale_err.log").read()[-1500:])
+PY
+  done
 done
