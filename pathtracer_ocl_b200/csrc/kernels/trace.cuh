@@ -237,6 +237,8 @@ template <typename R> struct Params {
     int slices;                 // sample slices per pixel: a power of two <= kBlockWarps * cluster size
     int slices_per_block;       // min(slices, kBlockWarps): the warps of a block are slices_per_block slices of
                                 // kBlockWarps / slices_per_block tiles; a cluster holds all slices of its tiles
+    int defer_below;
+    int defer_max;              // mesh walk: iterations a warp with fewer than four rays at the mesh may put the walk off (0 = never)
     int lane_walk_min;          // mesh walk: rays per warp from which every lane walks its own ray (mesh_hit_lanes); 33 = never
     int stack_entries;          // mesh walk: entries of one 8-lane group's stack in dynamic shared memory (scene's worst case + 1)
     R pi;                       // (double)3.14159265359f, tracer.cl:1
@@ -624,6 +626,7 @@ __device__ __forceinline__ void mesh_hit(const Params<R>& P, const DObjHot<R>& o
 // 4.13 / 2.84 / 9.91, 4.24 / 2.92 / 9.97, 4.26 / 2.94 / 9.71, 4.26 / 2.95 / 8.00 -- divergence and the local-memory
 // stacks make the private walk pay only when (nearly) the whole warp wants the mesh.
 constexpr int kLaneWalkMin = 30;
+constexpr int kDeferMax = 3;                   // see closest_mesh
 template <typename R>
 __device__ __forceinline__ void mesh_hit_lanes(const Params<R>& P, const DMesh<R>& m, int j, V3<R> o, V3<R> d, const Slab<R>& s, Hit<R>& h) {
     const R eps = P.eps;
@@ -691,30 +694,44 @@ __device__ __forceinline__ void mesh_hit_lanes(const Params<R>& P, const DMesh<R
 }
 
 // All mesh objects of the scene (tracer.cl:598-720), after the analytic objects.  Called by all 32 lanes.
+//
+// Deferral.  A cooperative round costs about as much as a whole analytic segment whether one or four of its groups
+// have a ray, and most rounds are under-filled: on the teapot 52 % of all rounds came from warps with one to three rays
+// at the mesh (gopher 35 %).  So a warp with fewer than four such rays may put the walk off: those lanes simply do
+// nothing this iteration -- no shading, no state change -- and repeat the segment in the next one (the analytic scan runs
+// for the other lanes anyway, and everything is a pure function of the path state), by which time more lanes have
+// usually reached the mesh and the rays share a round.  `defer_age` (warp-uniform) bounds how long a warp waits; it does
+// not wait when few other lanes are alive to make progress.  Returns true for a lane whose segment is put off.
 template <typename R>
-__device__ __forceinline__ void closest_mesh(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h, unsigned stk) {
-    {
-        for (int q = 0; q < P.n_mesh; ++q) {
-            const int j = P.mesh_obj[q];
-            const DObjHot<R>& ob = P.hot[j];
-            const DMesh<R>& m = P.mesh[j];
-            const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
-            const Slab<R> s = make_slab(d, P.eps);
-            R t0, t1, tn;
-            // object AABB under the reference rule (tracer.cl:609) AND the padded extent of the triangles within reach
-            // of the closest hit so far; NaN / inf rays hit nothing upstream
-            const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);
-            const bool want = live && finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1) &&
-                              keep_box(o, inv_dir(d), m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], h.t * R(1.0001), tn);
-            // (fp32 only: in double the private stacks and the second walk cost the kernel more registers than they save time)
-            if (sizeof(R) == 4 && __popc(__ballot_sync(kFullMask, want)) >= P.lane_walk_min) {
-                if (want) mesh_hit_lanes<R>(P, m, j, o, d, s, h);
-                __syncwarp();
-            } else {
-                mesh_hit<R>(P, ob, m, j, ro, rd, want, lane, h, stk);
-            }
+__device__ __forceinline__ bool closest_mesh(const Params<R>& P, V3<R> ro, V3<R> rd, bool live, int lane, Hit<R>& h, unsigned stk, int& defer_age) {
+    for (int q = 0; q < P.n_mesh; ++q) {
+        const int j = P.mesh_obj[q];
+        const DObjHot<R>& ob = P.hot[j];
+        const DMesh<R>& m = P.mesh[j];
+        const V3<R> o = xf_point(ob.inv, ro), d = xf_dir(ob.inv, rd);
+        const Slab<R> s = make_slab(d, P.eps);
+        R t0, t1, tn;
+        // object AABB under the reference rule (tracer.cl:609) AND the padded extent of the triangles within reach
+        // of the closest hit so far; NaN / inf rays hit nothing upstream
+        const bool finite = (o.x + o.y + o.z + d.x + d.y + d.z) * R(0) == R(0);
+        const bool want = live && finite && ray_box(o, d, s, ob.aux[0], ob.aux[1], ob.aux[2], ob.aux[3], ob.aux[4], ob.aux[5], t0, t1) &&
+                          keep_box(o, inv_dir(d), m.root_lo[0], m.root_hi[0], m.root_lo[1], m.root_hi[1], m.root_lo[2], m.root_hi[2], h.t * R(1.0001), tn);
+        const int n_want = __popc(__ballot_sync(kFullMask, want));
+        if (P.n_mesh == 1 && n_want > 0 && n_want < P.defer_below && defer_age < P.defer_max &&
+            __popc(__ballot_sync(kFullMask, live && !want)) >= 8) {
+            ++defer_age;
+            return want;
+        }
+        defer_age = 0;
+        // (fp32 only: in double the private stacks and the second walk cost the kernel more registers than they save time)
+        if (sizeof(R) == 4 && n_want >= P.lane_walk_min) {
+            if (want) mesh_hit_lanes<R>(P, m, j, o, d, s, h);
+            __syncwarp();
+        } else {
+            mesh_hit<R>(P, ob, m, j, ro, rd, want, lane, h, stk);
         }
     }
+    return false;
 }
 
 // A candidate of the slow loop: objects there are NOT visited in scene order relative to the fast slots, so the
@@ -1124,6 +1141,7 @@ __global__ void __launch_bounds__(kBlockThreads, NEE ? (sizeof(R) == 8 ? 2 : 4) 
     // pure function of (seed, sample, bounce), so evaluation order does not change any value.
     __shared__ R next_ray[6][kBlockThreads];          // the parked ray: written once and read once per path, so not in registers
     bool have_next = false;
+    int defer_age = 0;
     unsigned stack_base = GROUPS ? (unsigned)__cvta_generic_to_shared(mesh_stacks) + (threadIdx.x / kWide) * (unsigned)P.stack_entries * 8u : 0u;
     asm volatile("" : "+r"(stack_base));      // opaque: keep it in a register instead of re-deriving the shared window base at every pop
 
@@ -1152,16 +1170,17 @@ __global__ void __launch_bounds__(kBlockThreads, NEE ? (sizeof(R) == 8 ? 2 : 4) 
 
         Hit<R> h;
         closest_analytic<R>(P, s.ro, s.rd, h);
-        if (GROUPS) closest_mesh<R>(P, s.ro, s.rd, live, lane, h, stack_base);
+        bool deferred = false;                   // this lane's mesh walk was put off: it repeats the segment next iteration
+        if (GROUPS) deferred = closest_mesh<R>(P, s.ro, s.rd, live, lane, h, stack_base, defer_age);
 
-        bool done = live;                        // a miss ends the path (re-tracing it cannot hit either)
+        bool done = live && !deferred;           // a miss ends the path (re-tracing it cannot hit either)
         NeeInfo<R> ni;
         ni.on = false;
-        if (live && h.obj >= 0) done = shade_hit<R, RNG, NEE>(P, h, s, fgi, ni);
+        if (live && !deferred && h.obj >= 0) done = shade_hit<R, RNG, NEE>(P, h, s, fgi, ni);
         if constexpr (NEE) {
             // Next-event estimation, tracer.cl:786-825: one shadow ray per light towards a point of the light's bounding
             // sphere, for every lane whose bounce takes part; the shadow rays of a warp are traced together.
-            ni.on = ni.on && live && h.obj >= 0;
+            ni.on = ni.on && live && !deferred && h.obj >= 0;
             for (int q = 0; q < P.n_lights; ++q) {
                 const DLight<R>& L = P.light[q];
                 const unsigned l = (unsigned)L.obj;
@@ -1181,7 +1200,8 @@ __global__ void __launch_bounds__(kBlockThreads, NEE ? (sizeof(R) == 8 ? 2 : 4) 
                 if (__any_sync(kFullMask, test)) {
                     Hit<R> hs;
                     closest_analytic<R>(P, so, dir, hs);
-                    if (GROUPS) closest_mesh<R>(P, so, dir, test, lane, hs, stack_base);
+                    int never = 0x7fffffff;                          // shadow rays are not deferred
+                    if (GROUPS) closest_mesh<R>(P, so, dir, test, lane, hs, stack_base, never);
                     if (test && hs.obj == (int)l && hs.t > P.eps) {
                         const R att = R(1) - m_div(hs.t, m_sqrt(hs.t * hs.t + L.t0 * L.t0));
                         const V3<R> emis = {L.er, L.eg, L.eb};

@@ -702,6 +702,10 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     P.n_slow = s.n_slow; P.n_mesh = s.n_mesh;
     P.stack_entries = (s.stack_need + 1) | 1;          // odd: the four groups of a warp push to different banks
     P.lane_walk_min = ptk::kLaneWalkMin;
+    P.defer_max = ptk::kDeferMax;
+    P.defer_below = 4;
+    if (const char* ov = std::getenv("PTC_DEFER_BELOW")) P.defer_below = std::atoi(ov);
+    if (const char* ov = std::getenv("PTC_DEFER_MAX")) P.defer_max = std::atoi(ov);                // tuning override
     if (const char* ov = std::getenv("PTC_LANE_WALK_MIN")) P.lane_walk_min = std::atoi(ov);      // tuning override
     P.shade = static_cast<const ptk::DObjShade<R>*>(d.shade);
     P.lens = static_cast<const R*>(d.lens);
