@@ -222,6 +222,8 @@ template <typename R> struct Params {
     DTex tex[3];
     const double* seeds;        // one per OWNED pixel: local rows, row-major
     const int* row_map;         // local row -> frame row
+    const int* tile_order;      // launch position -> tile: expensive tiles first (see plan_tile_order / measured costs), or NULL
+    unsigned* tile_cost;        // per tile: clocks / 256 the slowest warp of the tile took in this launch (feeds the next launch's order), or NULL
     void* out;                  // RGBA result, double4 (float4 when out_f32) per pixel, row-major, `width` pixels per row
     const int* out_row;         // local row -> row of `out`; NULL: rows are packed in local order.  With a map `out` may be a
                                 // buffer shared by several devices (a peer device's memory, or another process's through
@@ -232,6 +234,7 @@ template <typename R> struct Params {
     DLight<R> light[kMaxObjects];   // next-event estimation: the emissive objects, scene order
     int n_lights;
     int rows;                   // local rows rendered by this device
+    int n_tiles;                // 8x4 pixel tiles of those rows
     int samples;                // total samples per pixel (enters the RNG seeding and the final weight)
     int sample_begin, sample_end;   // samples rendered by this launch: [begin, end) (0, samples for a full render)
     int slices;                 // sample slices per pixel: a power of two <= kBlockWarps * cluster size
@@ -1084,15 +1087,17 @@ __device__ __forceinline__ double cluster_ld_f64(unsigned addr) {
 // Frame geometry of a thread.  A warp covers an 8x4 pixel tile for one sample slice.  The warps of a block are
 // slices_per_block slices of kBlockWarps / slices_per_block consecutive tiles; the blocks of a cluster hold the
 // remaining slices of the same tiles (slice = cluster rank * slices_per_block + slice within the block).
-struct PixelSlot { int lx, ly, gy, slice; bool has_pixel; };
+struct PixelSlot { int lx, ly, gy, slice, tile; bool has_pixel; };
 template <typename R> __device__ __forceinline__ PixelSlot pixel_slot(const Params<R>& P, unsigned cluster_rank, unsigned cluster_size) {
     const int W = P.cam.width;
     const int tiles_x = (W + kTileW - 1) / kTileW;
     const int spb = P.slices_per_block;                       // 1, 2 or 4 (power of two <= kBlockWarps)
     const int tiles_per_block = kBlockWarps / spb;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = (int)(blockIdx.x / cluster_size) * tiles_per_block + w / spb;
+    const int slot = (int)(blockIdx.x / cluster_size) * tiles_per_block + w / spb;
+    const int tile = P.tile_order ? (slot < P.n_tiles ? P.tile_order[slot] : slot) : slot;
     PixelSlot s;
+    s.tile = tile;
     s.slice = (int)cluster_rank * spb + (w % spb);
     s.lx = (tile % tiles_x) * kTileW + (lane & (kTileW - 1));
     s.ly = (tile / tiles_x) * kTileH + (lane / kTileW);
@@ -1109,6 +1114,7 @@ template <typename R, int RNG, bool GROUPS, bool NEE = false>
 __global__ void __launch_bounds__(kBlockThreads, NEE ? (sizeof(R) == 8 ? 2 : 4) : (sizeof(R) == 8 ? (GROUPS ? PTK_MESH_MIN_BLOCKS_F64 : PTK_MIN_BLOCKS_F64) : (GROUPS ? PTK_MESH_MIN_BLOCKS : PTK_MIN_BLOCKS))) trace_kernel(const __grid_constant__ Params<R> P) {
     extern __shared__ int2 mesh_stacks[];       // GROUPS: one stack of P.stack_entries per 8-lane group (sized by the host from the scene's BVH)
     const unsigned cluster_size = cluster_nctarank(), cluster_rank = cluster_ctarank();
+    const long long clock_begin = clock64();
     const PixelSlot px = pixel_slot(P, cluster_rank, cluster_size);
     const int lane = threadIdx.x & 31;
     const int W = P.cam.width;
@@ -1222,6 +1228,7 @@ __global__ void __launch_bounds__(kBlockThreads, NEE ? (sizeof(R) == 8 ? 2 : 4) 
     // cluster through distributed shared memory -- and are summed in slice order (deterministic: the same order for
     // any grid shape), so no per-slice partial sums ever go to HBM.  The first slice's thread of the cluster's first
     // block owns the pixel's store; with out_frame_rows that store goes straight into the (possibly remote) frame.
+    if (P.tile_cost && lane == 0 && px.tile < P.n_tiles) atomicMax(&P.tile_cost[px.tile], (unsigned)((clock64() - clock_begin) >> 8));
     if (cluster_size > 1) cluster_sync(); else __syncthreads();
     const int spb = P.slices_per_block;
     const int w = threadIdx.x >> 5;

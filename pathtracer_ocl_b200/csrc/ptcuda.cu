@@ -557,6 +557,10 @@ struct DeviceState {
     void* tex[3] = {nullptr, nullptr, nullptr};
     double* seeds = nullptr;        // rows*W: the seeds of the rows this device owns
     int* row_map = nullptr;         // local row -> frame row
+    int* tile_order = nullptr;      // launch position -> tile (heavy tiles first), or NULL
+    unsigned* tile_cost = nullptr;  // per tile: slowest warp's clocks of the last launch
+    int n_tiles = 0;
+    bool order_measured = false;    // tile_order comes from measured costs (after the first full trace)
     int* out_row = nullptr;         // local row -> row of the buffer the kernel stores into (packed context rows / frame rows)
     double* out = nullptr;          // rows*W*4: this device's packed rows (unused while the kernel stores into a gather / frame buffer)
     double* acc = nullptr;          // rows*W*4 running sums of a progressive render
@@ -722,6 +726,9 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     for (int k = 0; k < 3; ++k) P.tex[k] = ptk::DTex{static_cast<const uchar4*>(d.tex[k]), c.tex_w[k], c.tex_h[k], c.tex_layers[k]};
     P.seeds = d.seeds;
     P.row_map = d.row_map;
+    P.tile_order = d.tile_order;
+    P.tile_cost = d.order_measured ? nullptr : d.tile_cost;
+    P.n_tiles = d.n_tiles;
     P.sample_begin = 0; P.sample_end = c.samples;
     P.rows = int(d.rows.size());
     P.samples = c.samples;
@@ -749,6 +756,14 @@ void launch_kernel(K kernel, dim3 grid, dim3 block, size_t smem, int cluster, cu
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = unsigned(cluster); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 1 : 0;
+    if (std::getenv("PTC_DEBUG_OCCUPANCY")) {
+        int clusters = 0, blocks = 0;
+        cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, int(block.x), smem);
+        std::fprintf(stderr, "[launch] grid %u cluster %d smem %zu: max active clusters %d (= %d blocks), blocks/SM by occupancy %d\n", grid.x, cluster, smem,
+                     clusters, clusters * cluster, blocks);
+        cudaGetLastError();
+    }
     CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, P));
 }
 
@@ -775,7 +790,7 @@ template <typename R> void launch(ptc_context& c, DeviceState& d, const HostScen
     const bool fast = c.rng_mode == PTC_RNG_FAST;
     dim3 grid((unsigned)((tiles + tiles_per_block - 1) / tiles_per_block * d.cluster), 1, 1);
     dim3 block(ptk::kBlockThreads, 1, 1);
-    const size_t smem = meshes ? size_t(ptk::kBlockThreads / ptk::kWide) * size_t(P.stack_entries) * sizeof(int2) : 0;
+    const size_t smem = meshes ? size_t(ptk::kBlockThreads / ptk::kWide) * size_t(P.stack_entries) * sizeof(int2) : 0;   // traversal stacks
     if (c.nee) {                  // the next-event-estimation kernels (parity RNG stream only, checked in open_impl)
         if (meshes) launch_kernel(ptk::trace_kernel<R, ptk::RNG_PARITY, true, true>, grid, block, smem, d.cluster, d.stream, P);
         else launch_kernel(ptk::trace_kernel<R, ptk::RNG_PARITY, false, true>, grid, block, smem, d.cluster, d.stream, P);
@@ -831,27 +846,86 @@ void destroy(ptc_context* c) {
 }
 
 // Sample slices per pixel for a device that owns `px` pixels.  Small frames cannot fill 148 SMs with one thread
-// per pixel, and blocks that live for the whole frame leave a long tail, so each pixel's samples are split into
-// interleaved slices; all slices of a pixel sit in one thread-block cluster (kBlockWarps per block), which reduces
-// them, so the count is a power of two <= kBlockWarps * kMaxCluster = 32.  Measured on one B200 (round 2, Gpaths/s):
+// per pixel, and blocks that live for all the samples of their tile leave a tail, so each pixel's samples are split
+// into interleaved slices; all slices of a pixel sit in one thread-block cluster (kBlockWarps per block), which
+// reduces them, so the count is a power of two <= kBlockWarps * kMaxCluster = 32.  Measured on one B200 (round 2):
 //   whole 1280x960 frame, slices 1 / 2 / 4 / 8 / 16 / 32: reference scene 12.72 / 12.89 / 12.96 / 12.99 / 12.42 / 12.36,
-//                                                          teapot 2.30 / 3.12 / 3.54 / 3.67 / 3.50 / 3.44;
-//   one 1/8 shard of it (the 8-GPU case), 4 / 8 / 16 / 32:  reference scene 24.3 / 23.8 / 24.5 / 24.5 ms,
-//                                                          teapot 154 / 106 / 89 / 83 ms.
-// Clusters above two blocks cost a few per cent (eight blocks have to become free in one GPC together), so analytic
-// scenes stay at 8 slices unless the frame is too small to fill the machine; scenes with meshes, whose pixels differ
-// several-fold in cost, want ~10 M threads in total.
+//                                                          teapot 2.30 / 3.12 / 3.54 / 3.67 / 3.50 / 3.44 Gpaths/s;
+//   one 1/8 shard of it (the 8-GPU case) with the tiles launched longest-first, 8 / 16 / 32 slices: teapot 76.5 / 77.4 /
+//   78.2 ms, gopher 106.4 / 110.7 / 111.7 ms (in frame order the gopher shard needed 32 slices: 142.6 / 120.6 / 111.8).
+// Eight slices = clusters of two blocks: cudaOccupancyMaxActiveClusters gives 1184 resident blocks for clusters of one or
+// two, 1136 for four or eight (the GPCs' SM counts are not multiples of the cluster size), and smaller clusters keep the
+// tail short only together with the launch order below.  More slices only when the frame is too small to fill the machine.
 int plan_slices(long long px, int sm_count, bool meshes, int samples) {
+    (void)meshes;
     const long long resident = (long long)sm_count * 1024;                        // threads at 8 blocks x 128 per SM
-    long long sl;
-    if (meshes) sl = std::max<long long>(8, px ? ((long long)sm_count * 2048 * 32 + px - 1) / px : 1);
-    else sl = px * 8 >= 2 * resident ? 8 : (px ? (4 * resident + px - 1) / px : 1);
+    long long sl = px * 8 >= 2 * resident ? 8 : (px ? (4 * resident + px - 1) / px : 1);
     if (const char* ov = std::getenv("PTC_SLICES")) sl = std::atoll(ov);    // tuning override
     const long long cap = std::min<long long>(samples, ptk::kBlockWarps * ptk::kMaxCluster);
     if (sl > cap) sl = cap;
     int pow2 = 1;
     while (2ll * pow2 <= sl) pow2 *= 2;
     return pow2;
+}
+
+// Launch order of a device's 8x4 pixel tiles.  Blocks start in launch order and live for all the samples of their tile,
+// and a tile that looks at a mesh costs several times a tile that looks at a wall, so the last blocks to finish decide
+// the kernel's tail -- on a 1/8-frame shard the eight shard kernels together took 10 % longer than the whole frame in one
+// launch.  Longest-first scheduling: tiles whose pixels overlap the screen-space bounding rectangle of a mesh object
+// (its object-space AABB through `transform` and the camera) are launched first, the cheap ones fill the end.
+// Returns an empty vector when there is nothing to reorder.  Order only: every tile is rendered exactly once.
+std::vector<int> plan_tile_order(const ptc_job& job, const std::vector<int>& rows) {
+    const auto* objs = static_cast<const ptw_object*>(job.objects);
+    const auto* cam = static_cast<const ptw_camera*>(job.camera);
+    const int W = cam->width;
+    // world -> view: inverse of the affine camera matrix (rows 0..2 of cam->inverse are [A | t])
+    const double* m = cam->inverse;
+    const double a[3][3] = {{m[0], m[1], m[2]}, {m[4], m[5], m[6]}, {m[8], m[9], m[10]}}, t[3] = {m[3], m[7], m[11]};
+    const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                       a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    if (!(std::fabs(det) > 1e-300) || !(cam->pixel_size > 0.0)) return {};
+    double inv[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c2 = 0; c2 < 3; ++c2) {
+            const int r1 = (c2 + 1) % 3, r2 = (c2 + 2) % 3, c1 = (r + 1) % 3, c3 = (r + 2) % 3;
+            inv[r][c2] = (a[r1][c1] * a[r2][c3] - a[r1][c3] * a[r2][c1]) / det;
+        }
+    struct Rect { double x0, y0, x1, y1; };
+    std::vector<Rect> rects;
+    for (int i = 0; i < job.n_objects; ++i) {
+        const ptw_object& o = objs[i];
+        if (o.type != 4 || o.child_count <= 0) continue;
+        Rect rc{1e300, 1e300, -1e300, -1e300};
+        bool whole = false;
+        for (int k = 0; k < 8 && !whole; ++k) {
+            const double p[3] = {k & 1 ? o.bb_max[0] : o.bb_min[0], k & 2 ? o.bb_max[1] : o.bb_min[1], k & 4 ? o.bb_max[2] : o.bb_min[2]};
+            double w3[3], v[3];
+            for (int r = 0; r < 3; ++r) w3[r] = o.transform[4 * r] * p[0] + o.transform[4 * r + 1] * p[1] + o.transform[4 * r + 2] * p[2] + o.transform[4 * r + 3] - t[r];
+            for (int r = 0; r < 3; ++r) v[r] = inv[r][0] * w3[0] + inv[r][1] * w3[1] + inv[r][2] * w3[2];
+            if (!(v[2] < -1e-6) || !std::isfinite(v[0] + v[1] + v[2])) { whole = true; break; }      // behind the camera: give up on a rectangle
+            const double x = (cam->half_width - v[0] / -v[2]) / cam->pixel_size, y = (cam->half_height - v[1] / -v[2]) / cam->pixel_size;
+            rc.x0 = std::min(rc.x0, x); rc.x1 = std::max(rc.x1, x); rc.y0 = std::min(rc.y0, y); rc.y1 = std::max(rc.y1, y);
+        }
+        if (whole) return {};
+        const double margin = 8.0 + (cam->aperture != 0.0 ? 0.05 * W : 0.0);
+        rects.push_back(Rect{rc.x0 - margin, rc.y0 - margin, rc.x1 + margin, rc.y1 + margin});
+    }
+    if (rects.empty()) return {};
+    const int tiles_x = (W + ptk::kTileW - 1) / ptk::kTileW, tiles_y = (int(rows.size()) + ptk::kTileH - 1) / ptk::kTileH;
+    std::vector<int> heavy, light;
+    for (int ty = 0; ty < tiles_y; ++ty) {
+        int r0 = 1 << 30, r1 = -1;
+        for (int k = ty * ptk::kTileH; k < (ty + 1) * ptk::kTileH && k < int(rows.size()); ++k) { r0 = std::min(r0, rows[size_t(k)]); r1 = std::max(r1, rows[size_t(k)]); }
+        for (int tx = 0; tx < tiles_x; ++tx) {
+            const double x0 = tx * ptk::kTileW, x1 = x0 + ptk::kTileW;
+            bool hit = false;
+            for (const Rect& rc : rects) hit = hit || (x1 >= rc.x0 && x0 <= rc.x1 && double(r1 + 1) >= rc.y0 && double(r0) <= rc.y1);
+            (hit ? heavy : light).push_back(ty * tiles_x + tx);
+        }
+    }
+    if (heavy.empty() || light.empty()) return {};
+    heavy.insert(heavy.end(), light.begin(), light.end());
+    return heavy;
 }
 
 ptc_context* open_impl(const ptc_job& job) {
@@ -934,6 +1008,16 @@ ptc_context* open_impl(const ptc_job& job) {
         d.seeds = static_cast<double*>(dmalloc(d, px * sizeof(double)));
         upload_seeds(d, job.seeds, c.width, h2d);
         d.row_map = static_cast<int*>(upload(d, d.rows, h2d));
+        d.n_tiles = ((c.width + ptk::kTileW - 1) / ptk::kTileW) * ((int(d.rows.size()) + ptk::kTileH - 1) / ptk::kTileH);
+        if (meshes && !std::getenv("PTC_NO_TILE_ORDER") && d.n_tiles > 0) {
+            // Launch order (scenes with meshes, whose tiles differ several-fold in cost; analytic scenes lose 1-4 % when their
+            // costlier tiles are bunched up and have no tail to win back): the geometric estimate first, measured clocks after.
+            std::vector<int> order = plan_tile_order(job, d.rows);
+            if (order.empty()) { order.resize(size_t(d.n_tiles)); for (int k = 0; k < d.n_tiles; ++k) order[size_t(k)] = k; }
+            d.tile_order = static_cast<int*>(upload(d, order, h2d));
+            d.tile_cost = static_cast<unsigned*>(dmalloc(d, size_t(d.n_tiles) * sizeof(unsigned)));
+            CUDA_OK(cudaMemsetAsync(d.tile_cost, 0, size_t(d.n_tiles) * sizeof(unsigned), d.stream));
+        }
         d.out_row = nd > 1 ? static_cast<int*>(upload(d, out_rows[size_t(i)], h2d)) : nullptr;
         d.out = static_cast<double*>(dmalloc(d, px * 4 * sizeof(double)));
         d.slices = plan_slices((long long)px, d.sm_count, meshes, c.samples);
@@ -967,11 +1051,50 @@ ptc_context* open_impl(const ptc_job& job) {
     return guard.release();
 }
 
+// Adaptive launch order.  A launch that records per-tile clocks (Params::tile_cost: how long the slowest warp of each
+// tile ran) lets the host sort the tiles longest-first for the launches that follow, which removes the tail that
+// expensive tiles leave when they happen to start late -- on a 1/8-frame shard of the gopher scene 142.6 -> 106.4 ms
+// at 8 slices, where the geometric estimate of plan_tile_order is too coarse.  Once per context.
+void adopt_measured_order(DeviceState& d) {
+    CUDA_OK(cudaSetDevice(d.device));
+    std::vector<unsigned> cost(size_t(d.n_tiles));
+    CUDA_OK(cudaMemcpyAsync(cost.data(), d.tile_cost, cost.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, d.stream));
+    CUDA_OK(cudaStreamSynchronize(d.stream));
+    std::vector<int> order(size_t(d.n_tiles));
+    for (int k = 0; k < d.n_tiles; ++k) order[size_t(k)] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[size_t(x)] > cost[size_t(y)]; });
+    CUDA_OK(cudaMemcpyAsync(d.tile_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+    CUDA_OK(cudaStreamSynchronize(d.stream));
+    d.order_measured = true;
+}
+
+constexpr int kProbeSamples = 4;            // samples of the cost probe
+constexpr int kProbeMinSamples = 128;       // renders shorter than this are not worth a probe
+
 void trace_impl(ptc_context& c, int begin, int end, bool accumulate) {
     c.stats.kernel_launches = 0;
     for (DeviceState& d : c.dev) {
         CUDA_OK(cudaSetDevice(d.device));
         CUDA_OK(cudaEventRecord(d.ev0, d.stream));
+    }
+    // First full render of a context: a probe of kProbeSamples samples per pixel (0.2 % of a 2048-spp frame) measures
+    // the tiles' relative cost, then the real launch starts the expensive ones first.  Its pixels are overwritten by
+    // the render; its time is part of kernel_ms.
+    if (!accumulate && end - begin >= kProbeMinSamples) {
+        bool probing = false;
+        for (DeviceState& d : c.dev) {
+            if (!d.tile_cost || d.order_measured || d.rows.empty()) continue;
+            CUDA_OK(cudaSetDevice(d.device));
+            if (c.precision == PTC_FP64) launch<double>(c, d, c.scene64, begin, begin + kProbeSamples, false);
+            else launch<float>(c, d, c.scene32, begin, begin + kProbeSamples, false);
+            probing = true;
+        }
+        if (probing)
+            for (DeviceState& d : c.dev)
+                if (d.tile_cost && !d.order_measured && !d.rows.empty()) adopt_measured_order(d);
+    }
+    for (DeviceState& d : c.dev) {
+        CUDA_OK(cudaSetDevice(d.device));
         if (c.precision == PTC_FP64) launch<double>(c, d, c.scene64, begin, end, accumulate);
         else launch<float>(c, d, c.scene32, begin, end, accumulate);
         CUDA_OK(cudaEventRecord(d.ev1, d.stream));
@@ -984,6 +1107,9 @@ void trace_impl(ptc_context& c, int begin, int end, bool accumulate) {
         if (d.last_ms > worst) worst = d.last_ms;
     }
     c.stats.kernel_ms = worst;
+    // progressive passes and short renders: the clocks of this launch order the next one
+    for (DeviceState& d : c.dev)
+        if (d.tile_cost && !d.order_measured && !d.rows.empty() && end - begin >= kProbeSamples) adopt_measured_order(d);
 }
 
 // The double frame of the context's rows on dev[0] when every device stored into the gather buffer; else NULL.
