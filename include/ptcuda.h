@@ -86,7 +86,8 @@ typedef struct ptc_job {
 
     /* Devices driven by THIS process.  NULL/0 => device 0 (the reference's --device-index
      * default).  With n_devices > 1 the frame is split across them as interleaved scanline
-     * tiles and gathered over NVLink peer copies before the single D2H readback. */
+     * tiles; every device's kernel stores its pixels straight into one buffer on the first
+     * device (NVLink peer stores), so the readback is a single D2H. */
     const int32_t *devices;
     int32_t        n_devices;
 

@@ -7,7 +7,7 @@
 // Render() (internal/app/tracer/pathtracer.go:19-30): build the scene, flatten it
 // (BuildSceneBufferCL), trace, write experiment.raw and out-<samples>-<W>x<H>.png.  The trace goes
 // through the C ABI of libptcuda; extra flags select what the reference cannot: --precision
-// fp32|fp64, --rng parity|fast, --devices 0,1,.. (multi-GPU in one process), --seed N.
+// fp32|fp64, --rng parity|fast, --devices 0,1,.. (multi-GPU in one process), --seed N, --nee, --cylinder-caps.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +26,7 @@ struct Config {   // cmd/configuration.go:5-16
     bool list_devices = false, list_scenes = false;
     std::string scene = "gopher";
     // extensions
-    int precision = PTC_FP32, rng_mode = PTC_RNG_PARITY;
+    int precision = PTC_FP32, rng_mode = PTC_RNG_PARITY, features = 0;
     unsigned long long seed = 0;
     bool seed_given = false;
     std::vector<int32_t> devices;
@@ -72,6 +72,8 @@ int main(int argc, char** argv) {
         else if (take(argc, argv, i, "device-index", v)) cfg.device_index = std::atoi(v.c_str());
         else if (a == "--list-devices") cfg.list_devices = true;
         else if (a == "--list-scenes") cfg.list_scenes = true;
+        else if (a == "--nee") cfg.features |= PTC_FEATURE_NEE;                       // tracer.cl:1168, commented out upstream
+        else if (a == "--cylinder-caps") cfg.features |= PTC_FEATURE_CYLINDER_CAPS;   // tracer.cl:437-444, disabled upstream
         else if (take(argc, argv, i, "precision", v)) cfg.precision = (v == "fp64") ? PTC_FP64 : PTC_FP32;
         else if (take(argc, argv, i, "rng", v)) cfg.rng_mode = (v == "fast") ? PTC_RNG_FAST : PTC_RNG_PARITY;
         else if (take(argc, argv, i, "seed", v)) { cfg.seed = std::strtoull(v.c_str(), nullptr, 0); cfg.seed_given = true; }
@@ -121,6 +123,7 @@ int main(int argc, char** argv) {
     job.samples = cfg.samples;
     job.precision = cfg.precision;
     job.rng_mode = cfg.rng_mode;
+    job.features = cfg.features;
     int32_t one = cfg.device_index;
     if (cfg.devices.empty()) { job.devices = &one; job.n_devices = 1; }
     else { job.devices = cfg.devices.data(); job.n_devices = (int32_t)cfg.devices.size(); }

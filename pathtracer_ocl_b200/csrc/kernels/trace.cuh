@@ -38,7 +38,7 @@
 #include "rng.cuh"
 
 #ifndef PTK_KERNEL_VERSION
-#define PTK_KERNEL_VERSION "r02v5"      // names the ncu captures under profiles/ that belong to this kernel source
+#define PTK_KERNEL_VERSION "r02v6"      // names the ncu captures under profiles/ that belong to this kernel source
 #endif
 
 namespace ptk {
