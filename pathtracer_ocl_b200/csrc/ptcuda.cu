@@ -560,7 +560,7 @@ struct DeviceState {
     int* tile_order = nullptr;      // launch position -> tile (heavy tiles first), or NULL
     unsigned* tile_cost = nullptr;  // per tile: slowest warp's clocks of the last launch
     int n_tiles = 0;
-    bool order_measured = false;    // tile_order comes from measured costs (after the first full trace)
+    int order_measured = 0;         // tile_order comes from: 0 the geometric estimate, 1 the cost probe, 2 the clocks of a full render
     int* out_row = nullptr;         // local row -> row of the buffer the kernel stores into (packed context rows / frame rows)
     double* out = nullptr;          // rows*W*4: this device's packed rows (unused while the kernel stores into a gather / frame buffer)
     double* acc = nullptr;          // rows*W*4 running sums of a progressive render
@@ -727,7 +727,7 @@ template <typename R> ptk::Params<R> make_params(const ptc_context& c, const Dev
     P.seeds = d.seeds;
     P.row_map = d.row_map;
     P.tile_order = d.tile_order;
-    P.tile_cost = d.order_measured ? nullptr : d.tile_cost;
+    P.tile_cost = d.order_measured < 2 ? d.tile_cost : nullptr;
     P.n_tiles = d.n_tiles;
     P.sample_begin = 0; P.sample_end = c.samples;
     P.rows = int(d.rows.size());
@@ -1015,8 +1015,10 @@ ptc_context* open_impl(const ptc_job& job) {
             std::vector<int> order = plan_tile_order(job, d.rows);
             if (order.empty()) { order.resize(size_t(d.n_tiles)); for (int k = 0; k < d.n_tiles; ++k) order[size_t(k)] = k; }
             d.tile_order = static_cast<int*>(upload(d, order, h2d));
-            d.tile_cost = static_cast<unsigned*>(dmalloc(d, size_t(d.n_tiles) * sizeof(unsigned)));
-            CUDA_OK(cudaMemsetAsync(d.tile_cost, 0, size_t(d.n_tiles) * sizeof(unsigned), d.stream));
+            if (!std::getenv("PTC_ORDER_GEOMETRIC_ONLY")) {
+                d.tile_cost = static_cast<unsigned*>(dmalloc(d, size_t(d.n_tiles) * sizeof(unsigned)));
+                CUDA_OK(cudaMemsetAsync(d.tile_cost, 0, size_t(d.n_tiles) * sizeof(unsigned), d.stream));
+            }
         }
         d.out_row = nd > 1 ? static_cast<int*>(upload(d, out_rows[size_t(i)], h2d)) : nullptr;
         d.out = static_cast<double*>(dmalloc(d, px * 4 * sizeof(double)));
@@ -1054,8 +1056,10 @@ ptc_context* open_impl(const ptc_job& job) {
 // Adaptive launch order.  A launch that records per-tile clocks (Params::tile_cost: how long the slowest warp of each
 // tile ran) lets the host sort the tiles longest-first for the launches that follow, which removes the tail that
 // expensive tiles leave when they happen to start late -- on a 1/8-frame shard of the gopher scene 142.6 -> 106.4 ms
-// at 8 slices, where the geometric estimate of plan_tile_order is too coarse.  Once per context.
-void adopt_measured_order(DeviceState& d) {
+// at 8 slices, where the geometric estimate of plan_tile_order is too coarse.  Twice per context: after the 4-sample
+// probe of the first render, and again after that render itself (2048 samples rank the tiles better than 4: with the
+// probe's order alone two of the teapot's eight shards ran 90 ms instead of 73).
+void adopt_measured_order(DeviceState& d, int level, int samples) {
     CUDA_OK(cudaSetDevice(d.device));
     std::vector<unsigned> cost(size_t(d.n_tiles));
     CUDA_OK(cudaMemcpyAsync(cost.data(), d.tile_cost, cost.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, d.stream));
@@ -1063,9 +1067,47 @@ void adopt_measured_order(DeviceState& d) {
     std::vector<int> order(size_t(d.n_tiles));
     for (int k = 0; k < d.n_tiles; ++k) order[size_t(k)] = k;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[size_t(x)] > cost[size_t(y)]; });
+    // Granularity.  A block lives for samples / slices samples of its tile, and no order can finish the launch before its
+    // longest block.  Launched first, that block may take up to nearly the whole launch for free (gopher 1/8-frame shards
+    // at 8 slices: longest block 88-103 ms of a 106 ms launch, and 8 slices beat 32: 106 vs 110 ms) -- but not more: on
+    // two of the teapot's eight shards the costliest tile's block WAS the launch (90 ms, the other shards 72).  So after a
+    // full render: if the longest block took more than the launch would need with its blocks packed perfectly (the sum of
+    // the tiles' times spread over the resident warps), later launches use twice the slices and measure again.  After the probe there is only a noisy one-sample estimate, so the rule is coarse: 16 slices on a shard-sized
+    // launch whose costliest 0.2 % of tiles are more than 5.5x the mean (the teapot shards that need it: 5.8-6.5, the
+    // others 5.0-5.2, gopher 4.7-5.2).
+    bool again = false;
+    if (!std::getenv("PTC_SLICES") && samples >= 32 && !cost.empty()) {
+        int sl = d.slices;
+        if (level >= 2 && d.last_ms > 0.f) {
+            int khz = 0;
+            cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d.device);
+            const double to_ms = 256.0 / std::max(1.0, double(khz));
+            const double longest_ms = double(cost[size_t(order[0])]) * to_ms;
+            double total = 0.0;
+            for (unsigned v : cost) total += double(v);
+            // the launch if its blocks packed perfectly: every tile keeps `slices` warps busy for about its slowest warp's time
+            const double balanced_ms = total * to_ms * double(d.slices) / (double(d.sm_count) * 32.0);
+            if (longest_ms > 1.08 * balanced_ms && sl < ptk::kBlockWarps * ptk::kMaxCluster) { sl *= 2; again = true; }
+            if (std::getenv("PTC_DEBUG_TIMING"))
+                std::fprintf(stderr, "[order] full render: longest block %.1f ms, balanced %.1f ms, launch %.1f ms at %d slices -> %d slices\n", longest_ms, balanced_ms, d.last_ms, d.slices, sl);
+        } else if (level == 1) {
+            const size_t top = std::max<size_t>(1, cost.size() / 500);
+            double sum = 0.0, sum_top = 0.0;
+            for (size_t k = 0; k < cost.size(); ++k) { sum += cost[size_t(order[k])]; if (k < top) sum_top += cost[size_t(order[k])]; }
+            const double r = sum > 0.0 ? (sum_top / double(top)) / (sum / double(cost.size())) : 0.0;
+            const double tiles_per_warp_slot = double(cost.size()) / (double(d.sm_count) * 32.0);      // few tiles per resident warp: a shard
+            if (r > 5.5 && tiles_per_warp_slot < 4.0) sl = std::max(sl, 16);
+            if (std::getenv("PTC_DEBUG_TIMING")) std::fprintf(stderr, "[order] probe: r = %.2f -> %d slices\n", r, sl);
+        }
+        while (sl > samples) sl /= 2;
+        d.slices = std::max(1, sl);
+        d.cluster = std::max(1, d.slices / ptk::kBlockWarps);
+    }
+    if (again) level = 1;                     // keep recording: the next full render checks the new granularity
     CUDA_OK(cudaMemcpyAsync(d.tile_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+    CUDA_OK(cudaMemsetAsync(d.tile_cost, 0, cost.size() * sizeof(unsigned), d.stream));       // the next recording starts from zero
     CUDA_OK(cudaStreamSynchronize(d.stream));
-    d.order_measured = true;
+    d.order_measured = level;
 }
 
 constexpr int kProbeSamples = 4;            // samples of the cost probe
@@ -1083,7 +1125,7 @@ void trace_impl(ptc_context& c, int begin, int end, bool accumulate) {
     if (!accumulate && end - begin >= kProbeMinSamples) {
         bool probing = false;
         for (DeviceState& d : c.dev) {
-            if (!d.tile_cost || d.order_measured || d.rows.empty()) continue;
+            if (!d.tile_cost || d.order_measured != 0 || d.rows.empty()) continue;
             CUDA_OK(cudaSetDevice(d.device));
             if (c.precision == PTC_FP64) launch<double>(c, d, c.scene64, begin, begin + kProbeSamples, false);
             else launch<float>(c, d, c.scene32, begin, begin + kProbeSamples, false);
@@ -1091,7 +1133,7 @@ void trace_impl(ptc_context& c, int begin, int end, bool accumulate) {
         }
         if (probing)
             for (DeviceState& d : c.dev)
-                if (d.tile_cost && !d.order_measured && !d.rows.empty()) adopt_measured_order(d);
+                if (d.tile_cost && d.order_measured == 0 && !d.rows.empty()) adopt_measured_order(d, 1, c.samples);
     }
     for (DeviceState& d : c.dev) {
         CUDA_OK(cudaSetDevice(d.device));
@@ -1107,9 +1149,10 @@ void trace_impl(ptc_context& c, int begin, int end, bool accumulate) {
         if (d.last_ms > worst) worst = d.last_ms;
     }
     c.stats.kernel_ms = worst;
-    // progressive passes and short renders: the clocks of this launch order the next one
+    // the clocks of this launch order the next ones (a full render: final; progressive passes and short renders: until a longer one)
     for (DeviceState& d : c.dev)
-        if (d.tile_cost && !d.order_measured && !d.rows.empty() && end - begin >= kProbeSamples) adopt_measured_order(d);
+        if (d.tile_cost && d.order_measured < 2 && !d.rows.empty() && end - begin >= kProbeSamples)
+            adopt_measured_order(d, end - begin >= kProbeMinSamples ? 2 : 1, c.samples);
 }
 
 // The double frame of the context's rows on dev[0] when every device stored into the gather buffer; else NULL.
