@@ -1,3 +1,5 @@
+"""Histogram of rays per warp that enter a mesh walk (teapot / gopher / cube-map scene at 64 spp), from a tuning build of the
+library: tools/ab_build.sh hist "-DPTK_HIST".  The evidence behind the deferral and the private walk."""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
