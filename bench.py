@@ -409,7 +409,8 @@ def measure(env, scene_name, W, H, spp, ap, fl, precision_name, rng_name, steps,
             t0 = time.perf_counter()
             one = T.render_scene(scene, spp, seeds, precision=precision, rng_mode=rng_mode, devices=list(range(world)))
             ms = (time.perf_counter() - t0) * 1e3
-            out["single_process_multi_gpu"] = {"bit_identical_to_gathered": bool(np.array_equal(one, gathered)), "ms": ms,
+            out["single_process_multi_gpu"] = {"bit_identical_to_gathered": bool(np.array_equal(one, gathered)),
+                                               "max_abs_diff": float(np.abs(one - gathered).max()), "ms": ms,
                                                "devices": world, "api": "ptc_render with ptc_job.devices = [0..N-1], one process"}
         env.barrier()
     ctx.close()

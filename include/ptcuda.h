@@ -30,6 +30,10 @@
  *   - thread-compatible: distinct contexts may be used concurrently.  The only process-wide state is a
  *     mutex-protected table of per-device memory pools (driver handles) that keeps a bounded amount of device
  *     memory between calls; ptc_trim() returns it.
+ *   - launch plan: a context may re-plan its launches after its first renders of a mesh scene (tile launch order and
+ *     sample slices per pixel, from measured per-tile clocks).  Pixels are pure functions of (scene, seeds, sample), so
+ *     only the order in which a pixel's samples are summed can change: fp64-mode results of a later render may differ
+ *     from the first in the last bits.  PTC_SLICES=<n> in the environment pins the slices.
  *   - arithmetic: PTC_FP64 evaluates tracer.cl's formulas in double but not operation by operation (fused multiply-add,
  *     reciprocal multiplies, spheres intersected in world space), so it agrees with the reference to the 1e-6 gate, not
  *     bit for bit; decisions that sit exactly on a threshold can differ.  Only the CPU oracle is bit-exact.

@@ -1621,6 +1621,31 @@ int ptc_debug_dfma_peak(int device, double* tflops, char* err, int errlen) {
     });
 }
 
+// Test hook (not part of the drop-in surface; host only, no device needed): the launch plan ptc_open would make for a
+// device with `sm_count` SMs that owns the job's shard -- sample slices per pixel and the initial (geometric) launch
+// order of its 8x4-pixel tiles.  Returns the number of tiles; fills at most `cap` entries of `order` (identity when the
+// scene has nothing to reorder); -1 with a message on a bad job.
+int ptc_debug_launch_plan(const ptc_job* job, int sm_count, int32_t* slices, int32_t* order, int cap, char* err, int errlen) {
+    int n_tiles = -1;
+    guarded(err, errlen, [&] {
+        if (!job) fail("job is NULL");
+        validate(*job);
+        const auto* cam = static_cast<const ptw_camera*>(job->camera);
+        const int rpt = job->rows_per_tile > 0 ? job->rows_per_tile : 4, sc = job->shard_count > 1 ? job->shard_count : 1;
+        const int si = job->shard_count > 1 ? job->shard_index : 0;
+        std::vector<int> rows;
+        for (int r = 0; r < cam->height; ++r) if ((r / rpt) % sc == si) rows.push_back(r);
+        HostScene<float> hs;
+        flatten<float>(*job, hs);
+        if (slices) *slices = plan_slices((long long)rows.size() * cam->width, sm_count, hs.n_mesh > 0, job->samples);
+        const int tiles = ((cam->width + ptk::kTileW - 1) / ptk::kTileW) * ((int(rows.size()) + ptk::kTileH - 1) / ptk::kTileH);
+        std::vector<int> plan = hs.n_mesh > 0 ? plan_tile_order(*job, rows) : std::vector<int>();
+        for (int k = 0; k < tiles && k < cap && order; ++k) order[k] = plan.empty() ? k : plan[size_t(k)];
+        n_tiles = tiles;
+    });
+    return n_tiles;
+}
+
 // Test hook (not part of the drop-in surface; host only, no device needed): flattens the job's scene in
 // double and copies one array of the rebuilt mesh index out, so tests can check the builder's invariants
 // (every triangle in exactly one leaf, child boxes containing their triangles, depth) and replay the walk.

@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
         L.ptc_frame_device_pointer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.ptc_frame_destroy.argtypes = [C.c_void_p]
         L.ptc_debug_dfma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int]
+        L.ptc_debug_launch_plan.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.ptc_debug_mesh_index.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_char_p, C.c_int]
         L.ptc_debug_mesh_index.restype = C.c_int64
         L.ptc_debug_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int]
@@ -429,6 +430,21 @@ _MESH_INDEX_ARRAYS = {  # name -> (selector, dtype, trailing shape)
     "node_lo": (6, np.float64, (4,)), "node_hi": (7, np.float64, (4,)), "node_parent": (8, np.int32, ()),
     "mesh": (9, np.float64, (8,)), "node_range": (10, np.int32, (2,)),
 }
+
+
+def debug_launch_plan(scene, samples: int, sm_count: int = 148, shard_index: int = 0, shard_count: int = 1, rows_per_tile: int = 0):
+    """Test hook (host only): (slices per pixel, initial launch order of the 8x4-pixel tiles) ptc_open would plan."""
+    seeds = np.zeros(scene.width * scene.height)
+    job = _Job(scene.objects, scene.triangles if scene.n_triangles else None, scene.groups if scene.n_groups else None,
+               scene.camera, None, None, None, seeds, samples, FP32, RNG_PARITY, None, shard_index, shard_count, rows_per_tile)
+    err = C.create_string_buffer(512)
+    slices = C.c_int32(0)
+    n = lib().ptc_debug_launch_plan(C.byref(job.struct), sm_count, C.byref(slices), None, 0, err, 512)
+    if n < 0:
+        raise PtcError(err.value.decode())
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    lib().ptc_debug_launch_plan(C.byref(job.struct), sm_count, C.byref(slices), order.ctypes.data, n, err, 512)
+    return int(slices.value), order[:n]
 
 
 def debug_mesh_index(scene) -> dict:

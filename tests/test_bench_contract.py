@@ -45,3 +45,19 @@ def test_reference_arm_on_a_mesh_scene():
     d = run(args=["--impl", "reference", "--steps", "1", "--warmup", "0", "--scene", "teapot", "--aperture", "0", "--focal-length", "0",
                   "--width", "64", "--height", "48", "--samples", "2"])[0]
     assert d["value"] > 0 and "teapot" in d["config"]["workload"]
+
+
+def test_config_table_matches_baseline_json():
+    """bench.py --config N must be BASELINE.json configs[N-1]: sizes and sample counts are checked against its text."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    configs = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    for key, idx in (("1", 0), ("2", 1), ("3", 2), ("4", 3), ("5", 4), ("5e", 4), ("5c", 4)):
+        scene, w, h, spp, ap, fl, label = bench.CONFIGS[key]
+        text = configs[idx]
+        assert f"{w}x{h}" in text and (f"{spp} spp" in text or f"@{spp}" in text.replace(" ", "") or f"at {spp} spp" in text), (key, text)
+        assert f"configs[{idx}]" in label
+    assert bench.CONFIGS["2"][4:6] == (0.15, 1.6) and "aperture 0.15" in configs[1] and "focal length 1.6" in configs[1]
+    assert bench.workload_name("reference", 1280, 960, 2048, 0.15, 1.6, bench.CONFIGS["2"][6]).startswith("reference scene 1280x960@2048spp")
