@@ -8,27 +8,33 @@
 // hash RNG (314-317) -- but organised for a Blackwell SM instead of mirroring the OpenCL source:
 //
 //   * one launch covers the whole frame (the reference enqueues H/4 four-scanline batches);
-//   * a thread owns a pixel (optionally a slice of its samples) and runs ONE flat loop whose
-//     iteration is a path segment: when a lane's path ends it regenerates the next camera ray in
-//     place, so lanes of a warp stay busy instead of idling until the longest path of the warp
-//     finishes (the reference nests samples x bounces per work-item);
+//   * a thread owns a pixel and a slice of its samples and runs ONE flat loop whose iteration is
+//     a path segment: when a lane's path ends it regenerates the next camera ray in place, so lanes
+//     of a warp stay busy instead of idling until the longest path of the warp finishes (the
+//     reference nests samples x bounces per work-item); the slices of a pixel are the warps of a
+//     block and the blocks of a thread-block cluster, and are summed through (distributed) shared
+//     memory in the kernel's epilogue -- one launch, one store per pixel, optionally straight into
+//     a frame on another GPU (the multi-GPU gather fused into the kernel);
 //   * closest hit is a running minimum in registers (the reference zero-fills a 6.9 KB `context`
 //     per bounce and scans it afterwards, tracer.cl:886, 727-741) and shading is fused into the
 //     segment loop (the reference stores bounces and replays them, 1071-1096 -> 1116-1179);
-//   * the per-object data the intersection loop needs (affine inverse, type, bounds) travels in the
-//     kernel parameter block, i.e. the constant bank: the loop index is warp-uniform, so the
-//     matrix entries are read through the uniform datapath and feed FFMA directly instead of
-//     costing load instructions and registers (the reference copies 16 KB of 1024-byte records
-//     into __local per work-item, tracer.cl:846-849); material data is fetched per hit;
+//   * the per-object data the intersection code needs travels in the kernel parameter block, i.e.
+//     the constant bank (the reference copies 16 KB of 1024-byte records into __local per
+//     work-item, tracer.cl:846-849): planes and spheres as 16-byte records of UNROLLED slots at
+//     fixed offsets -- no loop, no type dispatch, spheres intersected in world space -- the rest as
+//     affine inverse + bounds for a short loop; material data is fetched per hit;
 //   * mesh objects are re-indexed on the host by an 8-wide SAH BVH over the caller's own triangle
 //     records, walked cooperatively -- eight lanes share one ray, four rays per warp -- and every
 //     candidate hit is checked against the caller's BVH boxes so that exactly the triangles the
 //     reference's stack walk (tracer.cl:624-714) would have tested can win (see "mesh objects"
 //     below); nodes and triangles are 16-byte-vectorised records (48 B of test data per triangle
-//     instead of a 512-byte stride);
+//     instead of a 512-byte stride); warps with few rays at the mesh put the walk off so that rays
+//     share rounds, warps whose lanes all reach it walk one ray per lane, and the tiles that look
+//     at a mesh are launched first (the host orders them by measured clocks);
 //   * the depth-of-field lens points depend only on the sample index, so they come from a table
 //     built once on the host instead of two sqrt, a divide and a sincos per path;
-//   * everything is templated on the arithmetic type: float = "fp32 mode", double = tracer.cl.
+//   * everything is templated on the arithmetic type: float = "fp32 mode", double = tracer.cl's
+//     precision (its formulas, not its operation order: agreement to the 1e-6 gate, not bit for bit).
 //     The fp32 instantiation uses the SFU approximations (rcp / rsqrt / sqrt / sin / cos) for its
 //     own arithmetic; the RNG and the texture filter stay exactly rounded in both modes.
 #pragma once
@@ -1227,7 +1233,7 @@ __global__ void __launch_bounds__(kBlockThreads, NEE ? (sizeof(R) == 8 ? 2 : 4) 
     // Epilogue: the slices of a pixel meet here -- the warps of this block through shared memory, the blocks of the
     // cluster through distributed shared memory -- and are summed in slice order (deterministic: the same order for
     // any grid shape), so no per-slice partial sums ever go to HBM.  The first slice's thread of the cluster's first
-    // block owns the pixel's store; with out_frame_rows that store goes straight into the (possibly remote) frame.
+    // block owns the pixel's store; with an out_row map that store goes straight into the (possibly remote) frame.
     if (P.tile_cost && lane == 0 && px.tile < P.n_tiles) atomicMax(&P.tile_cost[px.tile], (unsigned)((clock64() - clock_begin) >> 8));
     if (cluster_size > 1) cluster_sync(); else __syncthreads();
     const int spb = P.slices_per_block;
