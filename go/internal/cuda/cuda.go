@@ -15,7 +15,8 @@
 // live, and internal/cuda itself builds with no OpenCL header, ICD or runtime present.
 //
 // NOTE: no Go toolchain exists in the image this was written in.  The C side of every call below is exercised,
-// with exactly these argument shapes, by tests/c_abi_smoke.c; the Go side has been checked by eye only.
+// with exactly these argument shapes, by tests/c_abi_smoke.c; the Go side has been checked by eye only.  The
+// generic functions contain no cgo calls (they only check sizes and take addresses; traceRaw does the rest).
 package cuda
 
 /*
@@ -104,6 +105,8 @@ func checkSize[R any](what string, want uintptr) {
 	}
 }
 
+// TraceWithOptions is Trace plus what the OpenCL path could not select.  The generic part only checks the record sizes
+// and takes addresses; every cgo call lives in the non-generic traceRaw below.
 func TraceWithOptions[O, T, G, Cam any](objects []O, triangles []T, groups []G, deviceIndex, samples int,
 	camera Cam, textures []image.Image, sphereTextures []image.Image, cubeTextures []image.Image, opt Options) []float64 {
 
@@ -114,11 +117,26 @@ func TraceWithOptions[O, T, G, Cam any](objects []O, triangles []T, groups []G, 
 	if len(objects) == 0 {
 		logrus.Fatalf("cuda.Trace: scene has no objects")
 	}
+	var triPtr, grpPtr unsafe.Pointer
+	if len(triangles) > 0 {
+		triPtr = unsafe.Pointer(&triangles[0])
+	}
+	if len(groups) > 0 {
+		grpPtr = unsafe.Pointer(&groups[0])
+	}
+	return traceRaw(unsafe.Pointer(&objects[0]), len(objects), triPtr, len(triangles), grpPtr, len(groups),
+		unsafe.Pointer(&camera), deviceIndex, samples, textures, sphereTextures, cubeTextures, opt)
+}
+
+// traceRaw passes the packed records (include/ptwire.h) to ptc_render_flat2.  camera points at a 256-byte CLCamera.
+func traceRaw(objects unsafe.Pointer, nObjects int, triangles unsafe.Pointer, nTriangles int, groups unsafe.Pointer, nGroups int,
+	camera unsafe.Pointer, deviceIndex, samples int, textures, sphereTextures, cubeTextures []image.Image, opt Options) []float64 {
+
 	// CLCamera starts with Width, Height int32 (ocltracer.go:86-87)
-	dims := (*[2]int32)(unsafe.Pointer(&camera))
+	dims := (*[2]int32)(camera)
 	width, height := int(dims[0]), int(dims[1])
 	numPixels := width * height
-	logrus.Infof("trace with %d objects %dx%d", len(objects), width, height)
+	logrus.Infof("trace with %d objects %dx%d", nObjects, width, height)
 
 	// one random double per pixel, as computeBatch does per batch (ocltracer.go:260-263)
 	seeds := opt.Seeds
@@ -129,7 +147,7 @@ func TraceWithOptions[O, T, G, Cam any](objects []O, triangles []T, groups []G, 
 		}
 	}
 
-	// Every buffer goes to C as a direct call argument (ptc_render_flat): cgo pins Go memory passed
+	// Every buffer goes to C as a direct call argument (ptc_render_flat2): cgo pins Go memory passed
 	// that way for the duration of the call, whereas storing Go pointers inside a C struct is not allowed.
 	var tex [3]*C.uint8_t
 	var texDims [9]C.int32_t
@@ -142,13 +160,6 @@ func TraceWithOptions[O, T, G, Cam any](objects []O, triangles []T, groups []G, 
 		keep[cls] = pix
 		tex[cls] = (*C.uint8_t)(unsafe.Pointer(&pix[0]))
 		texDims[3*cls], texDims[3*cls+1], texDims[3*cls+2] = C.int32_t(w), C.int32_t(h), C.int32_t(layers)
-	}
-	var triPtr, grpPtr unsafe.Pointer
-	if len(triangles) > 0 {
-		triPtr = unsafe.Pointer(&triangles[0])
-	}
-	if len(groups) > 0 {
-		grpPtr = unsafe.Pointer(&groups[0])
 	}
 	precision, rngMode := C.int32_t(C.PTC_FP32), C.int32_t(C.PTC_RNG_PARITY)
 	if opt.FP64 {
@@ -171,8 +182,8 @@ func TraceWithOptions[O, T, G, Cam any](objects []O, triangles []T, groups []G, 
 
 	results := make([]float64, numPixels*4)
 	errbuf := make([]byte, 512)
-	rc := C.ptc_render_flat2(unsafe.Pointer(&objects[0]), C.int32_t(len(objects)), triPtr, C.int32_t(len(triangles)),
-		grpPtr, C.int32_t(len(groups)), unsafe.Pointer(&camera), tex[0], tex[1], tex[2], &texDims[0],
+	rc := C.ptc_render_flat2(objects, C.int32_t(nObjects), triangles, C.int32_t(nTriangles),
+		groups, C.int32_t(nGroups), camera, tex[0], tex[1], tex[2], &texDims[0],
 		(*C.double)(unsafe.Pointer(&seeds[0])), C.int32_t(samples), precision, rngMode, features,
 		(*C.int32_t)(unsafe.Pointer(&devices[0])), C.int32_t(len(devices)),
 		(*C.double)(unsafe.Pointer(&results[0])), (*C.char)(unsafe.Pointer(&errbuf[0])), C.int(len(errbuf)))
