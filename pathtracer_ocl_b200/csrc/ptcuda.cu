@@ -17,9 +17,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <system_error>
+#include <thread>
 #include <vector>
 
 #include "../../include/ptcuda.h"
@@ -143,6 +146,15 @@ template <typename R> void padded(const Box3& b, R* lo, R* hi) {
 inline float code_as(float, int code) { float f; std::memcpy(&f, &code, 4); return f; }   // bit pattern, never used in arithmetic
 inline double code_as(double, int code) { return double(code); }                          // exact
 
+// Threads the BVH build may use: the host's, at most 4 (a 17 k-triangle mesh gains little beyond that -- the top
+// splits are serial passes -- and eight ranks of one box build at the same time); PTC_BUILD_THREADS overrides.
+// The tree does not depend on it.
+inline int build_threads() {
+    if (const char* ov = std::getenv("PTC_BUILD_THREADS")) return std::max(1, std::min(64, std::atoi(ov)));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return int(std::max(1u, std::min(4u, hw)));
+}
+
 template <typename R> struct BvhBuilder {
     const ptw_triangle* tris;
     HostScene<R>& out;
@@ -152,24 +164,25 @@ template <typename R> struct BvhBuilder {
     int bin_leaf = ptk::kLeafTris;      // triangles per leaf of the BINARY tree (1..kLeafTris); the optimal collapse wants a fine tree
     bool optimal = true;                // collapse by dynamic programming (see plan()); false: greedily by area
     static constexpr int kBins = 32, kSahDepth = 24;
+    static constexpr int kForkMin = 1024;       // ranges of at least this many triangles may hand one half to another thread
+    struct Bins { Box3 bb[3][kBins]; int bn[3][kBins] = {}; };   // split()'s scratch: clean on entry, cleaned before return
     // plan(): cost[n][i] = cheapest way to present binary subtree n as at most i+1 wide-BVH roots (i = 0..6)
     struct Plan { double cost[7]; signed char split[9]; bool leaf; };   // split[j]: roots given to the left child when n gets j (0 = "as j-1")
     std::vector<Plan> plans;
 
-    // binary SAH tree over prims[begin, end); returns the node's index in `bin`
-    int build(int begin, int end, int depth) {
-        const int me = int(bin.size());
-        bin.emplace_back();
-        Box3 box, cb;
+    // One step of the binary SAH build: bounds of prims[begin, end) into `box`, then either -1 (the range is a leaf)
+    // or the split position, with the range reordered around it.  Touches nothing outside the range and `s`.
+    int split(int begin, int end, int depth, Bins& s, Box3& box) {
+        Box3 cb;
+        box = Box3();
         for (int i = begin; i < end; ++i) { box.merge(prims[size_t(i)].box); cb.add(prims[size_t(i)].c); }
-        bin[size_t(me)].box = box; bin[size_t(me)].begin = begin; bin[size_t(me)].end = end;
         const int count = end - begin;
-        if (count <= bin_leaf) return me;
+        if (count <= bin_leaf) return -1;
         int mid = -1;
         const double ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
         if (depth < kSahDepth && (ext[0] > 0 || ext[1] > 0 || ext[2] > 0)) {
             double best = 1e300; int best_axis = -1, best_bin = -1;
-            Box3 bb[3][kBins]; int bn[3][kBins] = {};
+            unsigned occ[3] = {0u, 0u, 0u};                        // occupied bins per axis; the bins are clean outside them
             double scale3[3];
             for (int a = 0; a < 3; ++a) scale3[a] = ext[a] > 0 ? double(kBins) / ext[a] : 0.0;
             for (int i = begin; i < end; ++i) {                    // one pass bins the three axes
@@ -177,22 +190,34 @@ template <typename R> struct BvhBuilder {
                 for (int a = 0; a < 3; ++a) {
                     int k = int((p.c[a] - cb.lo[a]) * scale3[a]);
                     k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-                    bb[a][k].merge(p.box); bn[a][k]++;
+                    s.bb[a][k].merge(p.box); s.bn[a][k]++; occ[a] |= 1u << k;
                 }
             }
+            // The sweep visits occupied bins only.  Between two occupied bins both sides of the split hold the same
+            // triangles, so the cost repeats and (strict <) the first of the run -- the occupied bin -- is the one a
+            // sweep over all 32 bins would keep: same split, less work on the many small nodes.
             for (int a = 0; a < 3; ++a) {
-                if (!(ext[a] > 0)) continue;
-                double right_area[kBins]; int right_n[kBins];
-                Box3 acc; int n = 0;
-                for (int k = kBins - 1; k > 0; --k) { acc.merge(bb[a][k]); n += bn[a][k]; right_area[k] = acc.half_area(); right_n[k] = n; }
-                acc = Box3(); n = 0;
-                for (int k = 0; k < kBins - 1; ++k) {
-                    acc.merge(bb[a][k]); n += bn[a][k];
-                    if (n == 0 || right_n[k + 1] == 0) continue;
-                    // a leaf costs one cooperative step per started group of bin_leaf triangles
-                    const double cost = acc.half_area() * std::ceil(n / double(bin_leaf)) + right_area[k + 1] * std::ceil(right_n[k + 1] / double(bin_leaf));
-                    if (cost < best) { best = cost; best_axis = a; best_bin = k; }
+                if (ext[a] > 0) {
+                    double right_area[kBins]; int right_n[kBins];  // filled at occupied bins: everything from that bin up
+                    Box3 acc; int n = 0;
+                    for (unsigned m = occ[a]; m;) {
+                        const int k = 31 - __builtin_clz(m);
+                        m &= ~(1u << k);
+                        acc.merge(s.bb[a][k]); n += s.bn[a][k]; right_area[k] = acc.half_area(); right_n[k] = n;
+                    }
+                    acc = Box3(); n = 0;
+                    for (unsigned m = occ[a]; m;) {
+                        const int k = __builtin_ctz(m);
+                        m &= m - 1;
+                        if (!m) break;                             // the last occupied bin has nothing to its right
+                        const int next = __builtin_ctz(m);
+                        acc.merge(s.bb[a][k]); n += s.bn[a][k];
+                        // a leaf costs one cooperative step per started group of bin_leaf triangles
+                        const double cost = acc.half_area() * std::ceil(n / double(bin_leaf)) + right_area[next] * std::ceil(right_n[next] / double(bin_leaf));
+                        if (cost < best) { best = cost; best_axis = a; best_bin = k; }
+                    }
                 }
+                for (unsigned m = occ[a]; m; m &= m - 1) { const int k = __builtin_ctz(m); s.bb[a][k] = Box3(); s.bn[a][k] = 0; }
             }
             if (best_axis >= 0) {
                 const double scale = double(kBins) / ext[best_axis];
@@ -213,11 +238,61 @@ template <typename R> struct BvhBuilder {
             std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
                              [axis](const BuildPrim& x, const BuildPrim& y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.ref.rank < y.ref.rank); });
         }
-        const int l = build(begin, mid, depth + 1);
-        const int r = build(mid, end, depth + 1);
-        bin[size_t(me)].left = l; bin[size_t(me)].right = r;
-        bin[size_t(me)].height = 1 + std::max(bin[size_t(l)].height, bin[size_t(r)].height);
+        return mid;
+    }
+
+    // binary SAH tree over prims[begin, end), appended to `nodes` in preorder; returns the subtree's root index
+    int build(std::vector<BinNode>& nodes, Bins& s, int begin, int end, int depth) {
+        const int me = int(nodes.size());
+        nodes.emplace_back();
+        Box3 box;
+        const int mid = split(begin, end, depth, s, box);
+        nodes[size_t(me)].box = box; nodes[size_t(me)].begin = begin; nodes[size_t(me)].end = end;
+        if (mid < 0) return me;
+        const int l = build(nodes, s, begin, mid, depth + 1);
+        const int r = build(nodes, s, mid, end, depth + 1);
+        nodes[size_t(me)].left = l; nodes[size_t(me)].right = r;
+        nodes[size_t(me)].height = 1 + std::max(nodes[size_t(l)].height, nodes[size_t(r)].height);
         return me;
+    }
+
+    // The same tree with the two halves of large ranges built on different threads (they touch disjoint ranges of
+    // `prims`): every subtree comes back as its own preorder vector and is spliced in behind its parent, so node
+    // numbering -- and everything derived from it -- does not depend on the thread count.
+    std::vector<BinNode> grow(int begin, int end, int depth, int threads) {
+        std::vector<BinNode> nodes;
+        auto bins = std::make_unique<Bins>();
+        if (threads <= 1 || end - begin < kForkMin) {
+            nodes.reserve(size_t(2 * (end - begin) / std::max(1, bin_leaf) + 2));
+            build(nodes, *bins, begin, end, depth);
+            return nodes;
+        }
+        Box3 box;
+        const int mid = split(begin, end, depth, *bins, box);
+        nodes.emplace_back();
+        nodes[0].box = box; nodes[0].begin = begin; nodes[0].end = end;
+        if (mid < 0) return nodes;
+        int left_threads = int(double(threads) * double(mid - begin) / double(end - begin) + 0.5);
+        left_threads = std::max(1, std::min(threads - 1, left_threads));
+        std::future<std::vector<BinNode>> forked;
+        try {
+            forked = std::async(std::launch::async, [this, begin, mid, depth, left_threads] { return grow(begin, mid, depth + 1, left_threads); });
+        } catch (const std::system_error&) {}            // no thread to be had: this one does both halves
+        std::vector<BinNode> right = grow(mid, end, depth + 1, threads - left_threads);
+        std::vector<BinNode> left = forked.valid() ? forked.get() : grow(begin, mid, depth + 1, 1);
+        auto splice = [&nodes](const std::vector<BinNode>& sub) {
+            const int at = int(nodes.size());
+            for (BinNode n : sub) {
+                if (n.left >= 0) { n.left += at; n.right += at; }
+                nodes.push_back(n);
+            }
+            return at;
+        };
+        nodes.reserve(1 + left.size() + right.size());
+        const int l = splice(left), r = splice(right);
+        nodes[0].left = l; nodes[0].right = r;
+        nodes[0].height = 1 + std::max(nodes[size_t(l)].height, nodes[size_t(r)].height);
+        return nodes;
     }
 
     int make_leaf(const BinNode& n) {
@@ -362,14 +437,14 @@ void build_mesh(const ptw_object& s, int obj_index, const ptw_group* groups, int
     }
     if (prims.empty()) { m.bvh_root = -1; return; }
     BvhBuilder<R> builder{tris, out, prims};
-    builder.bin.reserve(prims.size());
     out.tri_test.reserve(out.tri_test.size() + 3 * prims.size()); out.tri_shade.reserve(out.tri_shade.size() + 3 * prims.size());
     out.tri_info.reserve(out.tri_info.size() + prims.size());
     out.wide.reserve(out.wide.size() + prims.size() * 2);
     if (const char* ov = std::getenv("PTC_BVH_BIN_LEAF")) builder.bin_leaf = std::max(1, std::min(ptk::kLeafTris, std::atoi(ov)));   // tuning overrides
     if (const char* ov = std::getenv("PTC_BVH_OPTIMAL")) builder.optimal = std::atoi(ov) != 0;
     const auto t_prims = Clock::now();
-    const int root = builder.build(0, int(prims.size()), 0);
+    builder.bin = builder.grow(0, int(prims.size()), 0, build_threads());
+    const int root = 0;
     const auto t_built = Clock::now();
     if (builder.optimal) { builder.plans.resize(builder.bin.size()); builder.plan(root); }
     const auto t_planned = Clock::now();

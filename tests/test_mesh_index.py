@@ -425,3 +425,18 @@ def test_replayed_walk_picks_the_winner_of_the_reference_kernels_own_walk(name, 
             hits += 1
             assert slot >= 0 and t == ref[i, 0], f"ray {i}: replay (slot {slot}, t {t!r}) vs reference t {ref[i, 0]!r}"
     assert hits > n_rays // 4
+
+
+def test_index_does_not_depend_on_the_build_thread_count(monkeypatch):
+    """ptc_open builds the halves of large triangle ranges on different threads (BvhBuilder::grow); subtrees are spliced
+    back in preorder, so every array of the index must be byte-identical whatever PTC_BUILD_THREADS says."""
+    scenes = [S.build_scene("gopher", 32, 24), geometric_mesh(3000, 0.99)]
+    for sc in scenes:
+        monkeypatch.setenv("PTC_BUILD_THREADS", "1")
+        want = T.debug_mesh_index(sc)
+        for threads in ("2", "3", "16"):
+            monkeypatch.setenv("PTC_BUILD_THREADS", threads)
+            got = T.debug_mesh_index(sc)
+            assert sorted(got) == sorted(want)
+            for k in want:
+                assert got[k].tobytes() == want[k].tobytes(), (threads, k)
