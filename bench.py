@@ -388,7 +388,8 @@ def measure(env, scene_name, W, H, spp, ap, fl, precision_name, rng_name, steps,
                 exchange.frame.read(pinned_out.data_ptr())
             c2.close()
 
-        e2e_step()
+        for _ in range(2):                 # untimed: the first one-shot calls of a process still grow the memory pool
+            e2e_step()
         env.barrier()
         e0 = time.perf_counter()
         for _ in range(steps):

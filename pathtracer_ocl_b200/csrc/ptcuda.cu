@@ -1052,10 +1052,8 @@ ptc_context* open_impl(const ptc_job& job) {
         ++local_tile;
     }
 
-    if (c.precision == PTC_FP64) flatten<double>(job, c.scene64);
-    else flatten<float>(job, c.scene32);
-    const bool meshes = (c.precision == PTC_FP64 ? c.scene64.n_mesh : c.scene32.n_mesh) > 0;
-
+    // Per device, first what does not depend on the flattened scene -- stream, pool, textures, seeds, row map -- so that
+    // (from pinned host memory) those copies run while the host builds the scene tables and the mesh index below.
     int64_t h2d = 0;
     for (int i = 0; i < nd; ++i) {
         DeviceState& d = c.dev[size_t(i)];
@@ -1070,8 +1068,6 @@ ptc_context* open_impl(const ptc_job& job) {
         if (nd == 1) d.pool = pool_for(d.device);
         CUDA_OK(cudaEventCreate(&d.ev0));
         CUDA_OK(cudaEventCreate(&d.ev1));
-        if (c.precision == PTC_FP64) upload_scene<double>(d, c.scene64, h2d);
-        else upload_scene<float>(d, c.scene32, h2d);
         for (int k = 0; k < 3; ++k) {
             if (!job.tex[k]) continue;
             size_t bytes = size_t(c.tex_w[k]) * c.tex_h[k] * c.tex_layers[k] * 4;
@@ -1083,6 +1079,18 @@ ptc_context* open_impl(const ptc_job& job) {
         d.seeds = static_cast<double*>(dmalloc(d, px * sizeof(double)));
         upload_seeds(d, job.seeds, c.width, h2d);
         d.row_map = static_cast<int*>(upload(d, d.rows, h2d));
+    }
+
+    if (c.precision == PTC_FP64) flatten<double>(job, c.scene64);
+    else flatten<float>(job, c.scene32);
+    const bool meshes = (c.precision == PTC_FP64 ? c.scene64.n_mesh : c.scene32.n_mesh) > 0;
+
+    for (int i = 0; i < nd; ++i) {
+        DeviceState& d = c.dev[size_t(i)];
+        CUDA_OK(cudaSetDevice(d.device));
+        if (c.precision == PTC_FP64) upload_scene<double>(d, c.scene64, h2d);
+        else upload_scene<float>(d, c.scene32, h2d);
+        const size_t px = d.rows.size() * size_t(c.width);
         d.n_tiles = ((c.width + ptk::kTileW - 1) / ptk::kTileW) * ((int(d.rows.size()) + ptk::kTileH - 1) / ptk::kTileH);
         if (meshes && !std::getenv("PTC_NO_TILE_ORDER") && d.n_tiles > 0) {
             // Launch order (scenes with meshes, whose tiles differ several-fold in cost; analytic scenes lose 1-4 % when their
